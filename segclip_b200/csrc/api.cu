@@ -1,0 +1,50 @@
+// Library-level plumbing: error text, launch counter, sc_gemm dispatch.
+#include <stdarg.h>
+
+#include <atomic>
+
+#include "common.cuh"
+
+static thread_local char g_err[512] = "";
+static std::atomic<long long> g_launches{0};
+
+void sc_set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+void sc_count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+int sc_num_sms() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess ||
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
+      n = 148;
+  }
+  return n;
+}
+
+int sc_gemm_tc(const sc_gemm_desc* d, cudaStream_t st);
+int sc_gemm_simt(const sc_gemm_desc* d, cudaStream_t st);
+
+extern "C" {
+
+const char* sc_last_error(void) { return g_err; }
+int sc_abi_version(void) { return SC_ABI_VERSION; }
+long long sc_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+
+int sc_gemm(const sc_gemm_desc* d, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  SC_CHECK_ARG(d && d->A && d->B && d->C, "sc_gemm: null operand");
+  SC_CHECK_ARG(d->M > 0 && d->N > 0 && d->K > 0, "sc_gemm: bad shape %d %d %d", d->M, d->N, d->K);
+  SC_CHECK_ARG(!(d->accumulate && d->c_dtype != SC_F32), "sc_gemm: accumulate needs fp32 C");
+  if (d->in_dtype == SC_BF16 && !d->force_simt) return sc_gemm_tc(d, st);
+  SC_CHECK_ARG(d->in_dtype == SC_F32 || d->in_dtype == SC_BF16, "sc_gemm: bad in_dtype %d", d->in_dtype);
+  return sc_gemm_simt(d, st);
+}
+
+}  // extern "C"

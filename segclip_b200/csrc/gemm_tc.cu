@@ -1,0 +1,430 @@
+// tcgen05 GEMM for sm_100a: C = epilogue(A * B^T), bf16 operands, fp32 accumulation in TMEM.
+//
+// One persistent CTA per SM, warp-specialised:
+//   warps 0-7  epilogue   (tcgen05.ld TMEM -> registers -> fused epilogue -> global)
+//   warp  8    TMA producer (cp.async.bulk.tensor, 128B swizzle, mbarrier expect-tx ring)
+//   warp  9    MMA issuer (single thread, tcgen05.mma.cta_group::1.kind::f16, 128 x BN x 16)
+// Tile 128 x BN x 64 (BN = 256 or 128), 4/6-stage smem ring, two TMEM accumulators so the
+// epilogue of tile i overlaps the main loop of tile i+1.  Operands may be K-major (row-major
+// [rows, K]) or MN-major (row-major [K, rows]); the latter serves dgrad (B = W) and wgrad
+// (A = dY, B = X) without materialising transposes.  Optional split-K accumulates with fp32
+// atomics (wgrad: K = batch*tokens, output only a few dozen tiles).
+#include <cuda.h>
+
+#include <mutex>
+#include <unordered_map>
+
+#include "common.cuh"
+#include "epilogue.cuh"
+
+namespace {
+
+constexpr int BM = 128;
+constexpr int BK = 64;  // 64 bf16 = 128 B = one swizzle row
+constexpr int NUM_EPI_WARPS = 8;
+constexpr int NUM_THREADS = (NUM_EPI_WARPS + 2) * 32;
+
+// ---------------------------------------------------------------------------------------------
+// PTX wrappers
+// ---------------------------------------------------------------------------------------------
+SC_DEVINL uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+SC_DEVINL void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+SC_DEVINL void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+               : "memory");
+}
+SC_DEVINL void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+SC_DEVINL void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t addr = smem_u32(bar);
+  uint32_t done = 0;
+  long long t0 = clock64();
+  while (true) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(addr), "r"(parity)
+        : "memory");
+    if (done) break;
+    if (clock64() - t0 > 4000000000LL) {  // ~2 s: a protocol bug, fail loudly instead of hanging
+      printf("segclip_b200 gemm_tc: mbarrier timeout (block %d thread %d)\n", blockIdx.x, threadIdx.x);
+      __trap();
+    }
+  }
+}
+SC_DEVINL void tma_load_2d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(dst)), "l"((uint64_t)map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+SC_DEVINL void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+SC_DEVINL void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+SC_DEVINL void tcgen05_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+SC_DEVINL void tcgen05_mma_f16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accum)
+      : "memory");
+}
+SC_DEVINL void tmem_ld32(uint32_t taddr, float* v) {
+  uint32_t* r = (uint32_t*)v;
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// Shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout), SWIZZLE_128B.
+//   K-major : rows of 128 B, 8-row swizzle atoms 1024 B apart (SBO); LBO unused (1).
+//   MN-major: 64-element (128 B) MN chunks; k rows 128 B apart, 8-k-row atoms SBO=1024 B apart,
+//             consecutive MN chunks LBO = 64 rows * 128 B = 8192 B apart (one TMA box each).
+template <bool MN_MAJOR>
+SC_DEVINL uint64_t make_smem_desc(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+  d |= (uint64_t)(MN_MAJOR ? (8192 >> 4) : 1) << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;  // descriptor version (Blackwell)
+  d |= (uint64_t)2 << 61;  // SWIZZLE_128B
+  return d;
+}
+
+template <int BN>
+struct TileCfg {
+  static constexpr int STAGES = (BN == 256) ? 4 : 6;
+  static constexpr int A_BYTES = BM * BK * 2;
+  static constexpr int B_BYTES = BN * BK * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int TMEM_COLS = 2 * BN;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+};
+
+template <int BN, bool A_MN, bool B_MN>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int tiles_m,
+               int tiles_n, int splits, int kb_total, int kb_per_split, EpiParams ep) {
+  using Cfg = TileCfg<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + Cfg::STAGES * Cfg::A_BYTES;
+  uint64_t* bars = (uint64_t*)(smem + Cfg::STAGES * Cfg::STAGE_BYTES);
+  uint64_t* full_bar = bars;
+  uint64_t* empty_bar = bars + Cfg::STAGES;
+  uint64_t* tmem_full = bars + 2 * Cfg::STAGES;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint32_t* tmem_slot = (uint32_t*)(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < Cfg::STAGES; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tmem_full[i], 1);
+      mbar_init(&tmem_empty[i], NUM_EPI_WARPS);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  if (warp == NUM_EPI_WARPS + 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "r"((uint32_t)Cfg::TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int num_items = tiles_m * tiles_n * splits;
+
+  if (warp == NUM_EPI_WARPS) {
+    // =============================== TMA producer ===============================
+    if (lane == 0) {
+      asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tmA) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tmB) : "memory");
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
+        const int nt = item % tiles_n;
+        const int mt = (item / tiles_n) % tiles_m;
+        const int sp = item / (tiles_n * tiles_m);
+        const int m0 = mt * BM, n0 = nt * BN;
+        const int kb0 = sp * kb_per_split;
+        const int kb1 = min(kb_total, kb0 + kb_per_split);
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          mbar_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
+          uint8_t* sa = smem_a + stage * Cfg::A_BYTES;
+          uint8_t* sb = smem_b + stage * Cfg::B_BYTES;
+          if (!A_MN) {
+            tma_load_2d(&tmA, &full_bar[stage], sa, kb * BK, m0);
+          } else {
+#pragma unroll
+            for (int j = 0; j < BM / 64; ++j) tma_load_2d(&tmA, &full_bar[stage], sa + j * 8192, m0 + j * 64, kb * BK);
+          }
+          if (!B_MN) {
+            tma_load_2d(&tmB, &full_bar[stage], sb, kb * BK, n0);
+          } else {
+#pragma unroll
+            for (int j = 0; j < BN / 64; ++j) tma_load_2d(&tmB, &full_bar[stage], sb + j * 8192, n0 + j * 64, kb * BK);
+          }
+          if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == NUM_EPI_WARPS + 1) {
+    // =============================== MMA issuer ===============================
+    if (lane == 0) {
+      // cute::UMMA::InstrDescriptor: c=f32 (bit4), a=b=bf16 (bits 7,10), majors (15,16), N>>3 (17), M>>4 (24)
+      constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((A_MN ? 1u : 0u) << 15) |
+                                 ((B_MN ? 1u : 0u) << 16) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+      constexpr uint32_t a_kstep = A_MN ? (16 * 128) >> 4 : (16 * 2) >> 4;  // descriptor units of 16 B per UMMA_K
+      constexpr uint32_t b_kstep = B_MN ? (16 * 128) >> 4 : (16 * 2) >> 4;
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int item = blockIdx.x; item < num_items; item += gridDim.x, ++it) {
+        const int sp = item / (tiles_n * tiles_m);
+        const int kb0 = sp * kb_per_split;
+        const int kb1 = min(kb_total, kb0 + kb_per_split);
+        const int acc = it & 1;
+        const uint32_t acc_phase = (it >> 1) & 1;
+        mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+        tcgen05_fence_after();
+        const uint32_t tmem_d = tmem_base + acc * BN;
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tcgen05_fence_after();
+          const uint64_t da = make_smem_desc<A_MN>(smem_u32(smem_a + stage * Cfg::A_BYTES));
+          const uint64_t db = make_smem_desc<B_MN>(smem_u32(smem_b + stage * Cfg::B_BYTES));
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) {
+            tcgen05_mma_f16(tmem_d, da + (uint64_t)(k * a_kstep), db + (uint64_t)(k * b_kstep), idesc,
+                            (kb > kb0 || k > 0) ? 1u : 0u);
+          }
+          tcgen05_commit(&empty_bar[stage]);  // frees the smem slot when these MMAs retire
+          if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
+        }
+        tcgen05_commit(&tmem_full[acc]);  // accumulator complete -> epilogue
+      }
+    }
+  } else {
+    // =============================== epilogue ===============================
+    const int quarter = warp & 3;       // TMEM lane quarter this warp may access
+    const int half = warp >> 2;         // column half of the tile
+    int it = 0;
+    for (int item = blockIdx.x; item < num_items; item += gridDim.x, ++it) {
+      const int nt = item % tiles_n;
+      const int mt = (item / tiles_n) % tiles_m;
+      const int m = mt * BM + quarter * 32 + lane;
+      const int nbase = nt * BN + half * (BN / 2);
+      const int acc = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1;
+      mbar_wait(&tmem_full[acc], acc_phase);
+      tcgen05_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BN + half * (BN / 2);
+#pragma unroll 1
+      for (int c = 0; c < BN / 2 / 32; ++c) {
+        float v[32];
+        tmem_ld32(taddr + c * 32, v);
+        if (m < ep.M) {
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            const int n = nbase + c * 32 + g * 8;
+            if (n < ep.N) epi_store8(ep, m, n, v + g * 8);
+          }
+        }
+      }
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+    }
+  }
+
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == NUM_EPI_WARPS + 1) {
+    tcgen05_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)Cfg::TMEM_COLS)
+                 : "memory");
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side: tensor-map cache + dispatch
+// ---------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)p;
+  });
+  return fn;
+}
+
+struct MapKey {
+  const void* ptr;
+  uint64_t d0, d1, stride;
+  uint32_t b0, b1;
+  bool operator==(const MapKey& o) const {
+    return ptr == o.ptr && d0 == o.d0 && d1 == o.d1 && stride == o.stride && b0 == o.b0 && b1 == o.b1;
+  }
+};
+struct MapKeyHash {
+  size_t operator()(const MapKey& k) const {
+    size_t h = (size_t)k.ptr;
+    h = h * 1000003u ^ k.d0;
+    h = h * 1000003u ^ k.d1;
+    h = h * 1000003u ^ k.stride;
+    h = h * 1000003u ^ ((uint64_t)k.b0 << 32 | k.b1);
+    return h;
+  }
+};
+
+// bf16 2-D tensor map, 128B swizzle, zero fill.  dim0 is the contiguous dimension.
+int get_tensor_map(const void* ptr, uint64_t dim0, uint64_t dim1, uint64_t stride_elems, uint32_t box0, uint32_t box1,
+                   CUtensorMap* out) {
+  static std::mutex mu;
+  static std::unordered_map<MapKey, CUtensorMap, MapKeyHash> cache;
+  MapKey key{ptr, dim0, dim1, stride_elems, box0, box1};
+  {
+    std::lock_guard<std::mutex> g(mu);
+    auto it = cache.find(key);
+    if (it != cache.end()) {
+      *out = it->second;
+      return SC_OK;
+    }
+  }
+  EncodeTiledFn enc = get_encode_fn();
+  if (!enc) {
+    sc_set_error("cuTensorMapEncodeTiled not available from the CUDA driver");
+    return SC_ERR_CUDA;
+  }
+  cuuint64_t gdim[2] = {dim0, dim1};
+  cuuint64_t gstride[1] = {stride_elems * 2};
+  cuuint32_t box[2] = {box0, box1};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), gdim, gstride, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    sc_set_error("cuTensorMapEncodeTiled failed (%d): ptr=%p dims=(%llu,%llu) stride=%llu box=(%u,%u)", (int)r, ptr,
+                 (unsigned long long)dim0, (unsigned long long)dim1, (unsigned long long)stride_elems, box0, box1);
+    return SC_ERR_CUDA;
+  }
+  std::lock_guard<std::mutex> g(mu);
+  if (cache.size() > 65536) cache.clear();
+  cache[key] = *out;
+  return SC_OK;
+}
+
+template <int BN, bool A_MN, bool B_MN>
+int launch(const sc_gemm_desc* d, const CUtensorMap& ta, const CUtensorMap& tb, int splits, cudaStream_t st) {
+  using Cfg = TileCfg<BN>;
+  auto kern = gemm_tc_kernel<BN, A_MN, B_MN>;
+  static bool configured = false;  // per template instantiation
+  if (!configured) {
+    SC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    configured = true;
+  }
+  const int tiles_m = ceil_div(d->M, BM), tiles_n = ceil_div(d->N, BN);
+  const int kb_total = ceil_div(d->K, BK);
+  int kb_per = ceil_div(kb_total, splits);
+  splits = ceil_div(kb_total, kb_per);  // no empty split
+  sc_gemm_desc dd = *d;
+  dd.split_k = splits;
+  EpiParams ep = make_epi(&dd);
+  const int items = tiles_m * tiles_n * splits;
+  const int grid = items < sc_num_sms() ? items : sc_num_sms();
+  kern<<<grid, NUM_THREADS, Cfg::SMEM_BYTES, st>>>(ta, tb, tiles_m, tiles_n, splits, kb_total, kb_per, ep);
+  SC_LAUNCH_CHECK();
+  return SC_OK;
+}
+
+}  // namespace
+
+extern void sc_count_launch(int n);
+
+// Returns SC_ERR_UNSUPPORTED when the problem does not meet the TMA alignment rules (caller falls
+// back to the FMA kernel only in fp32 mode; in bf16 mode this is an error).
+int sc_gemm_tc(const sc_gemm_desc* d, cudaStream_t st) {
+  const bool a_mn = d->trans_a != 0, b_mn = d->trans_b != 0;
+  auto aligned16 = [](const void* p) { return ((uintptr_t)p & 15) == 0; };
+  if (!(d->lda % 8 == 0 && d->ldb % 8 == 0 && aligned16(d->A) && aligned16(d->B) && d->N % 8 == 0 &&
+        d->ldc % 8 == 0 && aligned16(d->C) && (!d->C2 || aligned16(d->C2)) &&
+        (!d->bias || aligned16(d->bias)) && (!d->residual || (aligned16(d->residual) && d->ldr % 4 == 0)) &&
+        (!d->rowbias || (aligned16(d->rowbias) && d->ld_rowbias % 4 == 0)))) {
+    sc_set_error("sc_gemm(bf16): operands must be 16-byte aligned with leading dimensions multiple of 8 "
+                 "(M=%d N=%d K=%d lda=%lld ldb=%lld ldc=%lld)", d->M, d->N, d->K, (long long)d->lda,
+                 (long long)d->ldb, (long long)d->ldc);
+    return SC_ERR_UNSUPPORTED;
+  }
+  const int waste256 = ceil_div(d->N, 256) * 256 - d->N, waste128 = ceil_div(d->N, 128) * 128 - d->N;
+  const int BN = (waste256 <= waste128) ? 256 : 128;
+
+  const int kb_total = ceil_div(d->K, BK);
+  int splits = d->split_k;
+  if (splits < 0) {  // auto: fill roughly two waves of CTAs
+    const int tiles = ceil_div(d->M, BM) * ceil_div(d->N, BN);
+    splits = (2 * sc_num_sms() + tiles - 1) / tiles;
+    if (splits > kb_total / 4) splits = kb_total / 4;
+  }
+  if (splits < 1) splits = 1;
+  if (splits > kb_total) splits = kb_total;
+  if (splits > 1 && !(d->accumulate && d->c_dtype == SC_F32 && !d->C2)) {
+    sc_set_error("sc_gemm: split_k > 1 requires accumulate=1 into an fp32 C and no C2");
+    return SC_ERR_INVALID;
+  }
+
+  CUtensorMap ta, tb;
+  int rc;
+  if (!a_mn) rc = get_tensor_map(d->A, d->K, d->M, d->lda, BK, BM, &ta);
+  else rc = get_tensor_map(d->A, d->M, d->K, d->lda, 64, BK, &ta);
+  if (rc) return rc;
+  if (!b_mn) rc = get_tensor_map(d->B, d->K, d->N, d->ldb, BK, BN, &tb);
+  else rc = get_tensor_map(d->B, d->N, d->K, d->ldb, 64, BK, &tb);
+  if (rc) return rc;
+
+  sc_count_launch(1);
+#define SC_DISPATCH(BN_)                                                            \
+  if (!a_mn && !b_mn) return launch<BN_, false, false>(d, ta, tb, splits, st);      \
+  if (!a_mn && b_mn) return launch<BN_, false, true>(d, ta, tb, splits, st);        \
+  if (a_mn && b_mn) return launch<BN_, true, true>(d, ta, tb, splits, st);          \
+  return launch<BN_, true, false>(d, ta, tb, splits, st);
+  if (BN == 256) { SC_DISPATCH(256) }
+  SC_DISPATCH(128)
+#undef SC_DISPATCH
+}

@@ -1,0 +1,96 @@
+"""sc_gemm (tcgen05 bf16 kernel and fp32 FMA kernel) against a plain fp32 torch reference."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _ref(A, B, ta, tb, bias, rowbias, ridx, rmod, act, residual, alpha):
+    a = A.float().t() if ta else A.float()
+    b = B.float().t() if tb else B.float()
+    v = alpha * (a.double() @ b.double().t()).float()
+    if bias is not None:
+        v = v + bias
+    if rowbias is not None:
+        idx = ridx.long() if ridx is not None else torch.arange(v.shape[0], device=v.device) % rmod
+        v = v + rowbias[idx]
+    pre = v
+    if act == 1:
+        v = v * torch.sigmoid(1.702 * v)
+    elif act == 2:
+        v = torch.nn.functional.gelu(v)
+    if residual is not None:
+        v = v + residual
+    return v, pre
+
+
+def _run(M, N, K, dtype, ta=False, tb=False, bias=False, rowbias=0, ridx=False, act=0, residual=False,
+         c_dtype=torch.float32, c2=None, accumulate=False, split_k=0, alpha=1.0, force_simt=False, seed=0):
+    from segclip_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    dev = "cuda"
+    A = torch.randn((K, M) if ta else (M, K), device=dev, generator=g).to(dtype)
+    B = torch.randn((K, N) if tb else (N, K), device=dev, generator=g).to(dtype)
+    bias_t = torch.randn(N, device=dev, generator=g) if bias else None
+    rb = torch.randn(rowbias, N, device=dev, generator=g) if rowbias else None
+    ridx_t = torch.randint(0, rowbias, (M,), device=dev, generator=g, dtype=torch.int32) if (ridx and rowbias) else None
+    res = torch.randn(M, N, device=dev, generator=g) if residual else None
+    C0 = torch.randn(M, N, device=dev, generator=g) if accumulate else None
+    C = C0.clone() if accumulate else torch.full((M, N), float("nan"), device=dev, dtype=c_dtype)
+    C2 = torch.full((M, N), float("nan"), device=dev, dtype=c2) if c2 is not None else None
+    ops.gemm(A, B, C, trans_a=ta, trans_b=tb, bias=bias_t, rowbias=rb, rowbias_idx=ridx_t, act=act, residual=res,
+             C2=C2, accumulate=accumulate, split_k=split_k, alpha=alpha, force_simt=force_simt)
+    torch.cuda.synchronize()
+    want, pre = _ref(A, B, ta, tb, bias_t, rb, ridx_t, rowbias, act, res, alpha)
+    if accumulate:
+        want = want + C0
+    scale = float(want.abs().max()) + 1e-6
+    tol = 2e-5 if (dtype == torch.float32 and c_dtype == torch.float32) else (1e-2 if c_dtype == torch.bfloat16 else 2e-4)
+    err = float((C.float() - want).abs().max()) / scale
+    assert err < tol, (err, M, N, K, ta, tb)
+    if C2 is not None:
+        err2 = float((C2.float() - pre).abs().max()) / (float(pre.abs().max()) + 1e-6)
+        assert err2 < (1e-2 if c2 == torch.bfloat16 else 2e-4), err2
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 256, 64), (256, 256, 128), (128, 128, 64), (392, 768, 768), (300, 384, 200),
+                                   (50, 64, 72), (1000, 2304, 768), (16, 512, 512)])
+def test_tc_nt_plain(M, N, K):
+    _run(M, N, K, torch.bfloat16)
+
+
+@pytest.mark.parametrize("ta,tb", [(False, True), (True, True), (True, False)])
+@pytest.mark.parametrize("M,N,K", [(128, 256, 64), (256, 128, 192), (768, 768, 392), (3072, 768, 1000), (200, 328, 136)])
+def test_tc_transposed_operands(M, N, K, ta, tb):
+    _run(M, N, K, torch.bfloat16, ta=ta, tb=tb)
+
+
+def test_tc_epilogues():
+    _run(392, 3072, 768, torch.bfloat16, bias=True, act=1, c_dtype=torch.bfloat16, c2=torch.bfloat16)
+    _run(392, 768, 3072, torch.bfloat16, bias=True, residual=True)
+    _run(392, 768, 768, torch.bfloat16, rowbias=196)
+    _run(96, 768, 768, torch.bfloat16, rowbias=196, ridx=True, c_dtype=torch.bfloat16)
+    _run(16, 3072, 768, torch.bfloat16, bias=True, act=2, c_dtype=torch.bfloat16, c2=torch.bfloat16)
+    _run(256, 512, 512, torch.bfloat16, alpha=0.5, accumulate=True)
+
+
+def test_tc_split_k():
+    _run(768, 768, 8192, torch.bfloat16, ta=True, tb=True, accumulate=True, split_k=8)
+    _run(2304, 768, 5000, torch.bfloat16, ta=True, tb=True, accumulate=True, split_k=-1)
+    _run(768, 3072, 1568, torch.bfloat16, ta=True, tb=True, accumulate=True, split_k=-1)
+
+
+def test_tc_many_tiles_persistent():
+    # more tiles than SMs: exercises the smem ring / TMEM double-buffer phase logic
+    _run(8192, 2304, 768, torch.bfloat16, bias=True, c_dtype=torch.bfloat16)
+    _run(6272, 3072, 768, torch.bfloat16, bias=True, act=1, c_dtype=torch.bfloat16)
+
+
+@pytest.mark.parametrize("ta,tb", [(False, False), (False, True), (True, True)])
+def test_simt_fp32(ta, tb):
+    _run(200, 136, 77, torch.float32, ta=ta, tb=tb, bias=True, act=1, residual=True, c2=torch.float32)
+    _run(64, 8, 8, torch.float32, ta=ta, tb=tb, bias=True)
+
+
+def test_tc_matches_simt_on_bf16_inputs():
+    _run(300, 384, 200, torch.bfloat16, force_simt=True, bias=True)
