@@ -94,6 +94,243 @@ typedef struct {
 
 int sc_gemm(const sc_gemm_desc* d, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * LayerNorm (fp32 statistics).  Replaces LayerNorm.forward modules/module_clip_util.py:126-132 and
+ * the nn.LayerNorm calls at modules/module_seg_vit.py:288,297,300,312, modules/module_clip.py:86,129,
+ * modules/module_mae.py:196-197,317 and their autograd backward.
+ * y[map(r), :] = (x[r,:] - mean_r) * rstd_r * gamma + beta, with the optional row map
+ *   map(r) = (r / in_group) * out_group + out_off + r % in_group   (in_group == 0: identity)
+ * which writes straight into a concatenated buffer (kv_ = cat([q_feat, x]) module_seg_vit.py:294).
+ */
+typedef struct {
+  int64_t rows;
+  int32_t D;
+  const void* x;
+  int32_t x_dtype;
+  const float* gamma;
+  const float* beta;
+  float eps;
+  void* y;
+  int32_t y_dtype;
+  int32_t in_group, out_group, out_off;
+  float* mean; /* [rows] saved statistics (may be NULL) */
+  float* rstd;
+} sc_ln_desc;
+int sc_layernorm_fwd(const sc_ln_desc* d, void* stream);
+
+/* dx[r,:] (+)= LN-backward(dy[map(r),:]);  dgamma/dbeta (fp32 [D], caller-zeroed) accumulate
+ * atomically over rows and over calls. */
+typedef struct {
+  int64_t rows;
+  int32_t D;
+  const void* dy;
+  int32_t dy_dtype;
+  const void* x;
+  int32_t x_dtype;
+  const float* mean;
+  const float* rstd;
+  const float* gamma;
+  void* dx; /* may be NULL (only parameter gradients wanted) */
+  int32_t dx_dtype;
+  int32_t accumulate_dx;
+  void* dx_copy_bf16; /* optional bf16 copy of the final dx (operand of the next dgrad/wgrad GEMM) */
+  float* dgamma;
+  float* dbeta;
+  int32_t in_group, out_group, out_off;
+} sc_ln_bwd_desc;
+int sc_layernorm_bwd(const sc_ln_bwd_desc* d, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Attention core  o = softmax(scale * q k^T [+ causal mask]) v  per (batch slot, head).
+ * Replaces the bmm/softmax/bmm inside nn.MultiheadAttention (modules/module_seg_vit.py:189,215;
+ * modules/module_clip_ttransformer.py:46) and timm Attention (modules/module_mae.py:122-135).
+ * Element (b, i, h, d) of X is X[b*X_bs + i*X_rs + h*hd + d] (strides in elements), so packed QKV
+ * buffers and both centre-cross-attention K/V layouts ("torch18_flat" k_bs = row,
+ * k_rs = B rows; "per_sample" k_bs = Lk rows, k_rs = row) are expressed without copies.
+ * lse[b,h,i] = log sum_j exp(s_ij) is saved for the backward pass.
+ */
+typedef struct {
+  int32_t B, H, Lq, Lk, hd;
+  int32_t dtype; /* of q, k, v, o and their gradients */
+  int32_t causal;
+  float scale;
+  const void* q;
+  int64_t q_bs, q_rs;
+  const void* k;
+  int64_t k_bs, k_rs;
+  const void* v;
+  int64_t v_bs, v_rs;
+  void* o;
+  int64_t o_bs, o_rs;
+  float* lse; /* [B, H, Lq] */
+} sc_attn_desc;
+int sc_attention_fwd(const sc_attn_desc* a, void* stream);
+
+typedef struct {
+  sc_attn_desc fwd; /* same pointers as the forward call (o and lse are inputs here) */
+  const void* d_o;  /* strides of o */
+  void* d_q;        /* strides of q, k, v respectively */
+  void* d_k;
+  void* d_v;
+} sc_attn_bwd_desc;
+int sc_attention_bwd(const sc_attn_bwd_desc* g, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Element-wise / data-movement glue (all HBM-bound, one pass).
+ */
+/* dx = dy * act'(pre): autograd backward of QuickGELU / nn.GELU (module_clip_util.py:134-136). */
+int sc_act_bwd(const void* dy, int dy_dtype, const void* pre, int pre_dtype, void* dx, int dx_dtype, int64_t n, int act,
+               void* stream);
+/* dst = convert(src) * (scale_dev ? *scale_dev : 1): dtype conversion of residual-stream gradients and the final
+ * `grad * grad_output` hand-over to autograd (scale read on the device, no host sync). */
+int sc_convert(const void* src, int src_dtype, void* dst, int dst_dtype, int64_t n, const float* scale_dev, void* stream);
+/* out[c] += sum_r x[r*ld + c] (atomic): bias gradients of every nn.Linear on the path. */
+int sc_colsum(const void* x, int dtype, int64_t ld, int64_t rows, int cols, float* out, void* stream);
+
+/* fp32 master parameters -> compute-dtype shadow copies, one launch for the whole model
+ * (replaces the per-parameter `.type(self.dtype)` casts, modules/module_clip.py:84,109-112). */
+typedef struct {
+  const void* src; /* fp32 */
+  void* dst;
+  int64_t n;
+  int64_t first_block; /* prefix sum of ceil(n / 1024) */
+} sc_cast_item;
+int sc_cast_multi(const sc_cast_item* items_dev, int n_items, int64_t total_blocks, int dst_dtype, void* stream);
+
+/* nn.Conv1d(C, C, 1, groups) weight [C, C/groups] <-> dense block-diagonal [C, C]
+ * (k_conv / v_conv, modules/module_seg_vit.py:266-269,299,302). reduce: dw += diag blocks of dense. */
+int sc_blockdiag_expand(const float* w, void* dense, int C, int groups, int dtype, void* stream);
+int sc_blockdiag_reduce(const float* dense_grad, float* dw, int C, int groups, void* stream);
+
+/* Non-overlapping patch extraction for conv1 (kernel == stride, module_clip_vtransformer.py:21,56):
+ * out[r, c*p*p + y*p + x] = image[r / rows_per_img, c, (pid / grid)*p + y, (pid % grid)*p + x],
+ * pid = patch_idx ? patch_idx[r] : r % rows_per_img (MAE pass: only kept patches are embedded). */
+int sc_im2col(const float* image, void* out, int out_dtype, const int32_t* patch_idx, int64_t rows, int rows_per_img,
+              int grid, int patch, void* stream);
+
+/* token_embedding(ids) + positional_embedding (modules/module_clip.py:109-112) and the flat row index
+ * b*T + argmax_t ids[b,t] of the EOT token (:136). */
+int sc_text_embed(const int64_t* ids, const float* tok, const float* pos, float* out, int32_t* eot_rows, int B, int T,
+                  int W, void* stream);
+int sc_gather_rows(const float* src, const int32_t* idx, float* out, int64_t rows, int D, void* stream);
+int sc_scatter_rows(const float* src, const int32_t* idx, float* out, int64_t rows, int D, void* stream);
+
+/* random_masking(keep_cls=True) (modules/module_clip_util.py:91-124) from an explicit uniform draw u
+ * [B, L1]: ids_restore = argsort(argsort(noise)), ids_keep [B, keep], mask (1 = removed) and
+ * patch_idx [B, keep-1] = ids_keep[:,1:] - 1. */
+int sc_mae_mask(const float* u, int B, int L1, int keep, int32_t* ids_restore, int32_t* ids_keep, float* mask,
+                int32_t* patch_idx, void* stream);
+
+/* CLS := max over the G centre tokens (modules/module_seg_vit.py:441) and its backward routing. */
+int sc_pool_max(const float* x, float* out, int32_t* arg, int B, int G, int D, void* stream);
+int sc_pool_max_bwd(const float* dout, const int32_t* arg, float* dx, int B, int G, int D, void* stream);
+/* cat([mean(x, 1), x], 1) (modules/modeling.py:244-245) and backward. */
+int sc_mean_cat(const float* x, void* out, int out_dtype, int B, int n, int D, void* stream);
+int sc_mean_cat_bwd(const void* dout, int dout_dtype, float* dx, int B, int n, int D, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Patch -> centre aggregation (SemanticLearnerModule.forward, modules/module_seg_vit.py:304-312).
+ *   logits[b,g,l] = <qf[b,g,:], k[b,l,:]>                                   (:304)
+ *   y_soft = softmax((logits + Gumbel(u)) / tau, over g);  idx = argmax_g   (:221-237, tau = 0.9)
+ *   soft   = softmax(logits, over g)                                        (:306)
+ *   count[b,g] += #{l: idx = g}   (caller zeroes count)
+ * forced_idx (may be NULL) teacher-forces the arg-max (bf16 gradient parity tests).
+ */
+typedef struct {
+  int32_t B, G, L, D;
+  const float* qf; /* [B,G,D] cross_ln output */
+  const void* k;   /* [B,L,D] k_ln output */
+  int32_t k_dtype;
+  const float* u; /* [B,G,L] torch.rand draw behind the Gumbel noise */
+  float tau;
+  const int32_t* forced_idx; /* [B,L] or NULL */
+  float* logits;             /* [B,G,L] or NULL */
+  float* y_soft;             /* [B,G,L] */
+  float* soft;               /* [B,G,L] or NULL */
+  int32_t* idx;              /* [B,L] */
+  float* count;              /* [B,G] */
+} sc_assign_desc;
+int sc_assign_fwd(const sc_assign_desc* a, void* stream);
+
+/* agg[b,g,:] = sum_{l: idx=g} v[b,l,:] / max(count[b,g], 1) (:309-310); sum_out = qf + agg (:312). */
+int sc_aggregate_fwd(const void* v, int v_dtype, const int32_t* idx, const float* count, const float* qf, float* agg,
+                     float* sum_out, int B, int L, int D, void* stream);
+
+/* Backward of the three steps above given d_agg = d(sum_out):
+ *   d hard[g,l] = (<d_agg_g, v_l> - [count_g >= 1] <d_agg_g, agg_g>) / max(count_g,1) + d_hard_extra[g,l]
+ *   d logits    = y_soft * (d hard - sum_c y_soft_c d hard_c) / tau           (straight-through, :237)
+ *   d v[l,:]    = d_agg[idx_l,:] / max(count_idx_l, 1)
+ *   d k[l,:]    = sum_g d logits[g,l] qf[g,:];   d_qf = d_qf_base + sum_l d logits[g,l] k[l,:]
+ * d_hard_extra carries the superpixel-KL and ReconstructLayer gradients w.r.t. hard_attn. */
+typedef struct {
+  int32_t B, G, L, D;
+  const float* d_agg; /* [B,G,D] */
+  const float* agg;
+  const void* v;
+  int32_t v_dtype;
+  const int32_t* idx;
+  const float* count;
+  const float* y_soft;
+  const float* d_hard_extra; /* [B,G,L] or NULL */
+  float tau;
+  const float* qf;
+  const void* k;
+  int32_t k_dtype;
+  float* d_logits;         /* [B,G,L] scratch/out */
+  void* d_v;               /* [B,L,D] v_dtype */
+  void* d_k;               /* [B,L,D] k_dtype */
+  const float* d_qf_base;  /* [B,G,D] or NULL */
+  float* d_qf;             /* [B,G,D] */
+} sc_assign_bwd_desc;
+int sc_assign_bwd(const sc_assign_bwd_desc* a, void* stream);
+
+/* ReconstructLayer (modules/module_seg_vit.py:333-345) with a one-hot assignment:
+ *   pre[b,m,:] = sum_g' (W[g', idx[b,m]] + bias[g']) sx[b,g',:];  out = QuickGELU(pre)
+ * backward: d_sx, d hard[b,g,m] (into the d_hard_extra of sc_assign_bwd), dW / dbias (atomic +=). */
+int sc_reconstruct_fwd(const float* sx, const int32_t* idx, const float* W, const float* bias, float* pre, float* out,
+                       int B, int M, int D, void* stream);
+int sc_reconstruct_bwd(const float* d_out, const float* pre, const float* sx, const int32_t* idx, const float* W,
+                       const float* bias, float* d_sx, float* d_hard, float* dW, float* dbias, int B, int M, int D,
+                       void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Loss heads (modules/modeling.py:201-252).  Every loss term is atomically added into one device
+ * scalar `loss`; `gscale` is the upstream gradient (d total / d loss, normally 1).
+ */
+/* y = x / ||x||_2 per row (modeling.py:341-345) and backward. */
+int sc_l2norm_fwd(const float* x, float* y, float* inv_norm, int rows, int E, void* stream);
+int sc_l2norm_bwd(const float* dy, const float* y, const float* inv_norm, float* dx, int rows, int E, void* stream);
+
+/* InfoNCE, one direction (modeling.py:204-209,348-357).  raw = X_loc Y_all^T [B, N] (cosines, N = B*W);
+ * s = min(exp(*logit_scale_param), 100); labels = label_off + i with label_off = B*rank.
+ *   sc_ce_lse : lse[i] = logsumexp_j(s raw_ij);  loss += (lse_i - s raw_i,label) * 0.5 / B
+ *   sc_ce_grad: raw_ij <- s * gscale * 0.5/B * [ (softmax_own_ij - 1{j=label}) +
+ *                                                 (exp(s raw_ij - lse_other_all[j]) - 1{j=label}) ]
+ *     i.e. d loss / d (X_loc . Y_all) including the column terms that the reference obtains through
+ *     diffdist's reduce-scatter (modules/util_module.py:180-190) -- lse_other_all is the all-gathered
+ *     lse of the opposite direction, so no reduction collective is needed;
+ *     *d_logit_scale_param += sum_ij own-row gradient * raw_ij * d s/d p   (own rows only, like the reference). */
+int sc_ce_lse(const float* raw, int B, int N, int label_off, const float* logit_scale_param, float* lse, float* loss,
+              void* stream);
+int sc_ce_grad(float* raw, int B, int N, int label_off, const float* logit_scale_param, const float* lse_own,
+               const float* lse_other_all, float gscale, float* d_logit_scale_param, void* stream);
+
+/* Superpixel-KL head (modeling.py:212-224) on the hard assignment idx [B,L] and labels seg [B,L] (int64):
+ * loss += symmetric KL / (2 B L G);  d_hard[b,g,l] = d loss / d hard_attn[b,g,l] * gscale. */
+int sc_superpixel_kl(const int32_t* idx, const int64_t* seg, int B, int L, float gscale, float* loss, float* d_hard,
+                     void* stream);
+
+/* MAE decoder input assembly (modules/module_mae.py:306-311): x[b,i,:] = (r = ids_restore[b,i]) < keep ?
+ * emb[b,r,:] : mask_token, plus decoder_pos_embed[i,:]; and its backward. */
+int sc_mae_unshuffle(const void* emb, int emb_dtype, const float* mask_token, const int32_t* ids_restore, const float* pos,
+                     float* x, int B, int L1, int keep, int D, void* stream);
+int sc_mae_unshuffle_bwd(const float* dx, const int32_t* ids_restore, void* d_emb, int emb_dtype, float* d_mask_token, int B,
+                         int L1, int keep, int D, void* stream);
+/* Masked-patch MSE against patchify(image) (module_mae.py:18-29,322-328): loss += ...; dpred written for all
+ * L1 rows (zero for CLS / kept patches). */
+int sc_mae_loss(const void* pred, int dtype, const float* image, const float* mask, int B, int L1, int keep, int grid,
+                int patch, float gscale, float* loss, void* dpred, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -66,13 +66,13 @@ SC_DEVINL void st_any(void* p, long i, int dtype, float v) {
 // QuickGELU x*sigmoid(1.702x) (reference modules/module_clip_util.py:134-136),
 // exact erf GELU (nn.GELU default; reference modules/module_seg_vit.py:128, module_mae.py:151)
 SC_DEVINL float act_fwd(float x, int act) {
-  if (act == SC_ACT_QUICKGELU) return x / (1.0f + __expf(-1.702f * x));
+  if (act == SC_ACT_QUICKGELU) return __fdividef(x, 1.0f + __expf(-1.702f * x));
   if (act == SC_ACT_GELU_ERF) return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f));
   return x;
 }
 SC_DEVINL float act_grad(float x, int act) {
   if (act == SC_ACT_QUICKGELU) {
-    float s = 1.0f / (1.0f + __expf(-1.702f * x));
+    float s = __fdividef(1.0f, 1.0f + __expf(-1.702f * x));
     return s * (1.0f + 1.702f * x * (1.0f - s));
   }
   if (act == SC_ACT_GELU_ERF) {

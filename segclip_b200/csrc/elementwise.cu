@@ -1,0 +1,328 @@
+// HBM-bound glue kernels of the SegCLIP hot path: activation backward, bias gradients, parameter
+// shadow casts, patch extraction, embedding, row gather/scatter, MAE masking, pooling.
+// All are one-pass, coalesced along the feature dimension, fp32 math.
+#include "common.cuh"
+
+extern void sc_count_launch(int n);
+
+namespace {
+
+// ---------------------------------------------------------------- activation backward / convert / scale
+__global__ void act_bwd_kernel(const void* __restrict__ dy, int dy_dt, const void* __restrict__ pre, int pre_dt,
+                               void* __restrict__ dx, int dx_dt, long n, int act) {
+  long i = ((long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  for (int j = 0; j < 4 && i + j < n; ++j)
+    st_any(dx, i + j, dx_dt, ld_any(dy, i + j, dy_dt) * act_grad(ld_any(pre, i + j, pre_dt), act));
+}
+// dst = src * (scale ? *scale : 1)
+__global__ void convert_kernel(const void* __restrict__ src, int sdt, void* __restrict__ dst, int ddt, long n,
+                               const float* __restrict__ scale) {
+  const float s = scale ? *scale : 1.0f;
+  long i = ((long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  for (int j = 0; j < 4 && i + j < n; ++j) st_any(dst, i + j, ddt, ld_any(src, i + j, sdt) * s);
+}
+
+// ---------------------------------------------------------------- column sums (bias gradients)
+template <typename T>
+__global__ void __launch_bounds__(256) colsum_kernel(const T* __restrict__ x, long ld, long rows, int cols,
+                                                      float* __restrict__ out, int rows_per_block) {
+  __shared__ float red[8][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int col = blockIdx.x * 32 + tx;
+  const long r0 = (long)blockIdx.y * rows_per_block;
+  const long r1 = min(rows, r0 + rows_per_block);
+  float s = 0.f;
+  if (col < cols)
+    for (long r = r0 + ty; r < r1; r += 8) s += to_f32(x[r * ld + col]);
+  red[ty][tx] = s;
+  __syncthreads();
+  if (ty == 0) {
+#pragma unroll
+    for (int w = 1; w < 8; ++w) s += red[w][tx];
+    if (col < cols) atomicAdd(out + col, s);
+  }
+}
+
+// ---------------------------------------------------------------- multi-tensor cast fp32 -> T
+__global__ void cast_multi_kernel(const sc_cast_item* __restrict__ items, int n_items, int dst_dtype) {
+  // binary search the item that owns this block
+  int lo = 0, hi = n_items - 1;
+  const long blk = blockIdx.x;
+  while (lo < hi) {
+    int mid = (lo + hi + 1) >> 1;
+    if (items[mid].first_block <= blk) lo = mid; else hi = mid - 1;
+  }
+  const sc_cast_item it = items[lo];
+  long i = ((blk - it.first_block) * blockDim.x + threadIdx.x) * 4;
+  const float* s = (const float*)it.src;
+  for (int j = 0; j < 4 && i + j < it.n; ++j) st_any(it.dst, i + j, dst_dtype, s[i + j]);
+}
+
+// block-diagonal expansion of a grouped 1x1 conv weight [C, C/groups] -> dense [C, C]
+__global__ void blockdiag_expand_kernel(const float* __restrict__ w, void* __restrict__ out, int C, int cg, int dtype) {
+  long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long)C * C) return;
+  int o = i / C, c = i % C;
+  float v = (c / cg == o / cg) ? w[(long)o * cg + (c % cg)] : 0.f;
+  st_any(out, i, dtype, v);
+}
+// gradient: dW[o, j] += dDense[o, (o/cg)*cg + j]
+__global__ void blockdiag_reduce_kernel(const float* __restrict__ dense, float* __restrict__ dw, int C, int cg) {
+  long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long)C * cg) return;
+  int o = i / cg, j = i % cg;
+  dw[i] += dense[(long)o * C + (o / cg) * cg + j];
+}
+
+// ---------------------------------------------------------------- patch extraction (im2col for stride == kernel)
+template <typename T>
+__global__ void im2col_kernel(const float* __restrict__ img, T* __restrict__ out, const int* __restrict__ patch_idx,
+                              int rows_per_img, int grid, int p, int res) {
+  const long row = blockIdx.x;
+  const int b = row / rows_per_img;
+  const int pid = patch_idx ? patch_idx[row] : (int)(row % rows_per_img);
+  const int py0 = (pid / grid) * p, px0 = (pid % grid) * p;
+  const int K = 3 * p * p;
+  for (int k = threadIdx.x; k < K; k += blockDim.x) {
+    int c = k / (p * p), r = (k / p) % p, q = k % p;
+    out[row * K + k] = from_f32<T>(img[(((long)b * 3 + c) * res + py0 + r) * res + px0 + q]);
+  }
+}
+
+// ---------------------------------------------------------------- text embedding
+__global__ void embed_kernel(const long long* __restrict__ ids, const float* __restrict__ tok,
+                             const float* __restrict__ pos, float* __restrict__ out, int T, int W) {
+  const long row = blockIdx.x;
+  const long id = ids[row];
+  const int t = row % T;
+  for (int d = threadIdx.x; d < W; d += blockDim.x) out[row * W + d] = tok[id * W + d] + pos[(long)t * W + d];
+}
+
+__global__ void eot_index_kernel(const long long* __restrict__ ids, int* __restrict__ eot_rows, int B, int T) {
+  int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  long long best = ids[(long)b * T];
+  int arg = 0;
+  for (int t = 1; t < T; ++t) {
+    long long v = ids[(long)b * T + t];
+    if (v > best) { best = v; arg = t; }   // first maximum, like torch.argmax
+  }
+  eot_rows[b] = b * T + arg;
+}
+
+__global__ void gather_rows_kernel(const float* __restrict__ src, const int* __restrict__ idx, float* __restrict__ out, int D) {
+  const long r = blockIdx.x;
+  const long s = idx[r];
+  for (int d = threadIdx.x; d < D; d += blockDim.x) out[r * D + d] = src[s * D + d];
+}
+__global__ void scatter_rows_kernel(const float* __restrict__ src, const int* __restrict__ idx, float* __restrict__ out, int D) {
+  const long r = blockIdx.x;
+  const long s = idx[r];
+  for (int d = threadIdx.x; d < D; d += blockDim.x) out[s * D + d] = src[r * D + d];
+}
+
+// ---------------------------------------------------------------- MAE random masking by rank
+// ids_restore[b,i] = rank of noise[b,i] (noise[b,0] forced to -1); kept tokens have rank < keep.
+__global__ void mae_mask_kernel(const float* __restrict__ u, int L1, int keep, int* __restrict__ ids_restore,
+                                int* __restrict__ ids_keep, float* __restrict__ mask, int* __restrict__ patch_idx) {
+  extern __shared__ float nz[];
+  const int b = blockIdx.x;
+  for (int i = threadIdx.x; i < L1; i += blockDim.x) nz[i] = (i == 0) ? -1.f : u[(long)b * L1 + i];
+  __syncthreads();
+  for (int i = threadIdx.x; i < L1; i += blockDim.x) {
+    const float v = nz[i];
+    int rank = 0;
+    for (int j = 0; j < L1; ++j) rank += (nz[j] < v) || (nz[j] == v && j < i);
+    ids_restore[(long)b * L1 + i] = rank;
+    mask[(long)b * L1 + i] = rank < keep ? 0.f : 1.f;
+    if (rank < keep) {
+      ids_keep[(long)b * keep + rank] = i;
+      if (rank > 0) patch_idx[(long)b * (keep - 1) + rank - 1] = i - 1;   // CLS is always rank 0
+    }
+  }
+}
+
+// ---------------------------------------------------------------- pooling
+__global__ void pool_max_kernel(const float* __restrict__ x, float* __restrict__ out, int* __restrict__ arg, int G, int D) {
+  const int b = blockIdx.x;
+  for (int d = threadIdx.x; d < D; d += blockDim.x) {
+    float best = x[((long)b * G) * D + d];
+    int a = 0;
+    for (int g = 1; g < G; ++g) {
+      float v = x[((long)b * G + g) * D + d];
+      if (v > best) { best = v; a = g; }
+    }
+    out[(long)b * D + d] = best;
+    arg[(long)b * D + d] = a;
+  }
+}
+__global__ void pool_max_bwd_kernel(const float* __restrict__ dout, const int* __restrict__ arg, float* __restrict__ dx, int G, int D) {
+  const int b = blockIdx.x;
+  for (int d = threadIdx.x; d < D; d += blockDim.x) {
+    const int a = arg[(long)b * D + d];
+    const float g0 = dout[(long)b * D + d];
+    for (int g = 0; g < G; ++g) dx[((long)b * G + g) * D + d] = (g == a) ? g0 : 0.f;
+  }
+}
+// out[b,0,:] = mean_l x[b,l,:]; out[b,1+l,:] = x[b,l,:]
+__global__ void mean_cat_kernel(const float* __restrict__ x, void* __restrict__ out, int n, int D, int dtype) {
+  const int b = blockIdx.x;
+  for (int d = threadIdx.x; d < D; d += blockDim.x) {
+    float s = 0.f;
+    for (int l = 0; l < n; ++l) {
+      float v = x[((long)b * n + l) * D + d];
+      s += v;
+      st_any(out, ((long)b * (n + 1) + 1 + l) * D + d, dtype, v);
+    }
+    st_any(out, ((long)b * (n + 1)) * D + d, dtype, s / n);
+  }
+}
+__global__ void mean_cat_bwd_kernel(const void* __restrict__ dout, float* __restrict__ dx, int n, int D, int dtype) {
+  const int b = blockIdx.x;
+  for (int d = threadIdx.x; d < D; d += blockDim.x) {
+    const float m = ld_any(dout, ((long)b * (n + 1)) * D + d, dtype) / n;
+    for (int l = 0; l < n; ++l) dx[((long)b * n + l) * D + d] = ld_any(dout, ((long)b * (n + 1) + 1 + l) * D + d, dtype) + m;
+  }
+}
+
+}  // namespace
+
+extern "C" {
+
+int sc_act_bwd(const void* dy, int dy_dtype, const void* pre, int pre_dtype, void* dx, int dx_dtype, int64_t n, int act,
+               void* stream) {
+  SC_CHECK_ARG(dy && pre && dx && n > 0, "sc_act_bwd: bad args");
+  sc_count_launch(1);
+  act_bwd_kernel<<<ceil_div(n, 4 * 256), 256, 0, (cudaStream_t)stream>>>(dy, dy_dtype, pre, pre_dtype, dx, dx_dtype, n, act);
+  SC_LAUNCH_CHECK();
+  return SC_OK;
+}
+
+int sc_convert(const void* src, int src_dtype, void* dst, int dst_dtype, int64_t n, const float* scale_dev, void* stream) {
+  SC_CHECK_ARG(src && dst && n > 0, "sc_convert: bad args");
+  sc_count_launch(1);
+  convert_kernel<<<ceil_div(n, 4 * 256), 256, 0, (cudaStream_t)stream>>>(src, src_dtype, dst, dst_dtype, n, scale_dev);
+  SC_LAUNCH_CHECK();
+  return SC_OK;
+}
+
+int sc_colsum(const void* x, int dtype, int64_t ld, int64_t rows, int cols, float* out, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  SC_CHECK_ARG(x && out && rows > 0 && cols > 0, "sc_colsum: bad args");
+  const int gx = ceil_div(cols, 32);
+  int gy = (int)((4L * sc_num_sms() + gx - 1) / gx);
+  if (gy > ceil_div(rows, 64)) gy = ceil_div(rows, 64);
+  if (gy < 1) gy = 1;
+  const int rpb = ceil_div(rows, gy);
+  gy = ceil_div(rows, rpb);
+  sc_count_launch(1);
+  if (dtype == SC_F32) colsum_kernel<float><<<dim3(gx, gy), 256, 0, st>>>((const float*)x, ld, rows, cols, out, rpb);
+  else colsum_kernel<bf16><<<dim3(gx, gy), 256, 0, st>>>((const bf16*)x, ld, rows, cols, out, rpb);
+  SC_LAUNCH_CHECK();
+  return SC_OK;
+}
+
+int sc_cast_multi(const sc_cast_item* items_dev, int n_items, int64_t total_blocks, int dst_dtype, void* stream) {
+  SC_CHECK_ARG(items_dev && n_items > 0 && total_blocks > 0, "sc_cast_multi: bad args");
+  sc_count_launch(1);
+  cast_multi_kernel<<<(unsigned)total_blocks, 256, 0, (cudaStream_t)stream>>>(items_dev, n_items, dst_dtype);
+  SC_LAUNCH_CHECK();
+  return SC_OK;
+}
+
+int sc_blockdiag_expand(const float* w, void* dense, int C, int groups, int dtype, void* stream) {
+  SC_CHECK_ARG(w && dense && C % groups == 0, "sc_blockdiag_expand: bad args");
+  sc_count_launch(1);
+  blockdiag_expand_kernel<<<ceil_div((long)C * C, 256), 256, 0, (cudaStream_t)stream>>>(w, dense, C, C / groups, dtype);
+  SC_LAUNCH_CHECK();
+  return SC_OK;
+}
+
+int sc_blockdiag_reduce(const float* dense_grad, float* dw, int C, int groups, void* stream) {
+  SC_CHECK_ARG(dense_grad && dw && C % groups == 0, "sc_blockdiag_reduce: bad args");
+  sc_count_launch(1);
+  blockdiag_reduce_kernel<<<ceil_div((long)C * (C / groups), 256), 256, 0, (cudaStream_t)stream>>>(dense_grad, dw, C, C / groups);
+  SC_LAUNCH_CHECK();
+  return SC_OK;
+}
+
+int sc_im2col(const float* image, void* out, int out_dtype, const int32_t* patch_idx, int64_t rows, int rows_per_img,
+              int grid, int patch, void* stream) {
+  SC_CHECK_ARG(image && out && rows > 0, "sc_im2col: bad args");
+  sc_count_launch(1);
+  if (out_dtype == SC_F32)
+    im2col_kernel<float><<<(unsigned)rows, 256, 0, (cudaStream_t)stream>>>(image, (float*)out, patch_idx, rows_per_img, grid, patch, grid * patch);
+  else
+    im2col_kernel<bf16><<<(unsigned)rows, 256, 0, (cudaStream_t)stream>>>(image, (bf16*)out, patch_idx, rows_per_img, grid, patch, grid * patch);
+  SC_LAUNCH_CHECK();
+  return SC_OK;
+}
+
+int sc_text_embed(const int64_t* ids, const float* tok, const float* pos, float* out, int32_t* eot_rows, int B, int T,
+                  int W, void* stream) {
+  SC_CHECK_ARG(ids && tok && pos && out && eot_rows, "sc_text_embed: null pointer");
+  sc_count_launch(2);
+  embed_kernel<<<B * T, 128, 0, (cudaStream_t)stream>>>((const long long*)ids, tok, pos, out, T, W);
+  eot_index_kernel<<<ceil_div(B, 128), 128, 0, (cudaStream_t)stream>>>((const long long*)ids, eot_rows, B, T);
+  SC_LAUNCH_CHECK();
+  return SC_OK;
+}
+
+int sc_gather_rows(const float* src, const int32_t* idx, float* out, int64_t rows, int D, void* stream) {
+  SC_CHECK_ARG(src && idx && out && rows > 0, "sc_gather_rows: bad args");
+  sc_count_launch(1);
+  gather_rows_kernel<<<(unsigned)rows, 128, 0, (cudaStream_t)stream>>>(src, idx, out, D);
+  SC_LAUNCH_CHECK();
+  return SC_OK;
+}
+
+int sc_scatter_rows(const float* src, const int32_t* idx, float* out, int64_t rows, int D, void* stream) {
+  SC_CHECK_ARG(src && idx && out && rows > 0, "sc_scatter_rows: bad args");
+  sc_count_launch(1);
+  scatter_rows_kernel<<<(unsigned)rows, 128, 0, (cudaStream_t)stream>>>(src, idx, out, D);
+  SC_LAUNCH_CHECK();
+  return SC_OK;
+}
+
+int sc_mae_mask(const float* u, int B, int L1, int keep, int32_t* ids_restore, int32_t* ids_keep, float* mask,
+                int32_t* patch_idx, void* stream) {
+  SC_CHECK_ARG(u && ids_restore && ids_keep && mask && patch_idx && keep >= 1 && keep <= L1, "sc_mae_mask: bad args");
+  sc_count_launch(1);
+  mae_mask_kernel<<<B, 256, L1 * sizeof(float), (cudaStream_t)stream>>>(u, L1, keep, ids_restore, ids_keep, mask, patch_idx);
+  SC_LAUNCH_CHECK();
+  return SC_OK;
+}
+
+int sc_pool_max(const float* x, float* out, int32_t* arg, int B, int G, int D, void* stream) {
+  SC_CHECK_ARG(x && out && arg, "sc_pool_max: null pointer");
+  sc_count_launch(1);
+  pool_max_kernel<<<B, 256, 0, (cudaStream_t)stream>>>(x, out, arg, G, D);
+  SC_LAUNCH_CHECK();
+  return SC_OK;
+}
+
+int sc_pool_max_bwd(const float* dout, const int32_t* arg, float* dx, int B, int G, int D, void* stream) {
+  SC_CHECK_ARG(dout && dx && arg, "sc_pool_max_bwd: null pointer");
+  sc_count_launch(1);
+  pool_max_bwd_kernel<<<B, 256, 0, (cudaStream_t)stream>>>(dout, arg, dx, G, D);
+  SC_LAUNCH_CHECK();
+  return SC_OK;
+}
+
+int sc_mean_cat(const float* x, void* out, int out_dtype, int B, int n, int D, void* stream) {
+  SC_CHECK_ARG(x && out, "sc_mean_cat: null pointer");
+  sc_count_launch(1);
+  mean_cat_kernel<<<B, 256, 0, (cudaStream_t)stream>>>(x, out, n, D, out_dtype);
+  SC_LAUNCH_CHECK();
+  return SC_OK;
+}
+
+int sc_mean_cat_bwd(const void* dout, int dout_dtype, float* dx, int B, int n, int D, void* stream) {
+  SC_CHECK_ARG(dout && dx, "sc_mean_cat_bwd: null pointer");
+  sc_count_launch(1);
+  mean_cat_bwd_kernel<<<B, 256, 0, (cudaStream_t)stream>>>(dout, dx, n, D, dout_dtype);
+  SC_LAUNCH_CHECK();
+  return SC_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,231 @@
+// LayerNorm forward / backward (one warp per row, the row lives in registers).
+// Replaces modules/module_clip_util.py:126-132 (LayerNorm, fp32 statistics) and the nn.LayerNorm
+// instances in modules/module_seg_vit.py:256,264,267,272 and modules/module_mae.py:146,149,239.
+// HBM-bound: read x once, write y once (fwd); read dy, x once, write dx once (bwd).
+#include "common.cuh"
+
+namespace {
+
+template <typename T> SC_DEVINL float4 load4(const T* p, long i4);
+template <> SC_DEVINL float4 load4<float>(const float* p, long i4) { return *(const float4*)(p + i4 * 4); }
+template <> SC_DEVINL float4 load4<bf16>(const bf16* p, long i4) {
+  uint2 u = *(const uint2*)(p + i4 * 4);
+  __nv_bfloat162 a = *(__nv_bfloat162*)&u.x, b = *(__nv_bfloat162*)&u.y;
+  float2 fa = __bfloat1622float2(a), fb = __bfloat1622float2(b);
+  return make_float4(fa.x, fa.y, fb.x, fb.y);
+}
+template <typename T> SC_DEVINL void store4(T* p, long i4, float4 v);
+template <> SC_DEVINL void store4<float>(float* p, long i4, float4 v) { *(float4*)(p + i4 * 4) = v; }
+template <> SC_DEVINL void store4<bf16>(bf16* p, long i4, float4 v) {
+  __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y), b = __floats2bfloat162_rn(v.z, v.w);
+  uint2 u;
+  u.x = *(uint32_t*)&a;
+  u.y = *(uint32_t*)&b;
+  *(uint2*)(p + i4 * 4) = u;
+}
+
+SC_DEVINL long remap_row(long r, int in_group, int out_group, int out_off) {
+  if (in_group <= 0) return r;
+  return (r / in_group) * (long)out_group + out_off + (r % in_group);
+}
+
+template <typename TX, typename TY, int NV>
+__global__ void __launch_bounds__(256) ln_fwd_kernel(sc_ln_desc d) {
+  const int lane = threadIdx.x & 31;
+  const long row = (long)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (row >= d.rows) return;
+  const int D4 = d.D >> 2;
+  const TX* x = (const TX*)d.x + row * d.D;
+  float4 v[NV];
+  float s = 0.f;
+#pragma unroll
+  for (int j = 0; j < NV; ++j) {
+    int i4 = lane + 32 * j;
+    v[j] = (i4 < D4) ? load4<TX>(x, i4) : make_float4(0.f, 0.f, 0.f, 0.f);
+    s += v[j].x + v[j].y + v[j].z + v[j].w;
+  }
+  const float mean = warp_sum(s) / d.D;
+  float q = 0.f;
+#pragma unroll
+  for (int j = 0; j < NV; ++j) {
+    int i4 = lane + 32 * j;
+    if (i4 < D4) {
+      float a = v[j].x - mean, b = v[j].y - mean, c = v[j].z - mean, e = v[j].w - mean;
+      q += a * a + b * b + c * c + e * e;
+    }
+  }
+  const float rstd = rsqrtf(warp_sum(q) / d.D + d.eps);
+  if (lane == 0) {
+    if (d.mean) d.mean[row] = mean;
+    if (d.rstd) d.rstd[row] = rstd;
+  }
+  TY* y = (TY*)d.y + remap_row(row, d.in_group, d.out_group, d.out_off) * d.D;
+#pragma unroll
+  for (int j = 0; j < NV; ++j) {
+    int i4 = lane + 32 * j;
+    if (i4 < D4) {
+      float4 g = *(const float4*)(d.gamma + i4 * 4), b = *(const float4*)(d.beta + i4 * 4);
+      float4 o;
+      o.x = (v[j].x - mean) * rstd * g.x + b.x;
+      o.y = (v[j].y - mean) * rstd * g.y + b.y;
+      o.z = (v[j].z - mean) * rstd * g.z + b.z;
+      o.w = (v[j].w - mean) * rstd * g.w + b.w;
+      store4<TY>(y, i4, o);
+    }
+  }
+}
+
+template <typename TDY, typename TX, typename TDX, int NV>
+__global__ void __launch_bounds__(256) ln_bwd_kernel(sc_ln_bwd_desc d) {
+  __shared__ float red[8][32 * 4 + 1];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int D4 = d.D >> 2;
+  float4 dg[NV], db[NV];
+#pragma unroll
+  for (int j = 0; j < NV; ++j) dg[j] = db[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+
+  for (long row = (long)blockIdx.x * 8 + warp; row < d.rows; row += (long)gridDim.x * 8) {
+    const TX* x = (const TX*)d.x + row * d.D;
+    const TDY* dy = (const TDY*)d.dy + remap_row(row, d.in_group, d.out_group, d.out_off) * d.D;
+    const float mean = d.mean[row], rstd = d.rstd[row];
+    float4 xh[NV], g[NV];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int j = 0; j < NV; ++j) {
+      int i4 = lane + 32 * j;
+      if (i4 < D4) {
+        float4 xv = load4<TX>(x, i4), dv = load4<TDY>(dy, i4), gm = *(const float4*)(d.gamma + i4 * 4);
+        xh[j] = make_float4((xv.x - mean) * rstd, (xv.y - mean) * rstd, (xv.z - mean) * rstd, (xv.w - mean) * rstd);
+        g[j] = make_float4(dv.x * gm.x, dv.y * gm.y, dv.z * gm.z, dv.w * gm.w);
+        s1 += g[j].x + g[j].y + g[j].z + g[j].w;
+        s2 += g[j].x * xh[j].x + g[j].y * xh[j].y + g[j].z * xh[j].z + g[j].w * xh[j].w;
+        dg[j].x += dv.x * xh[j].x; dg[j].y += dv.y * xh[j].y; dg[j].z += dv.z * xh[j].z; dg[j].w += dv.w * xh[j].w;
+        db[j].x += dv.x; db[j].y += dv.y; db[j].z += dv.z; db[j].w += dv.w;
+      } else {
+        xh[j] = g[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    }
+    const float c1 = warp_sum(s1) / d.D, c2 = warp_sum(s2) / d.D;
+    if (d.dx) {
+      TDX* dx = (TDX*)d.dx + row * d.D;
+#pragma unroll
+      for (int j = 0; j < NV; ++j) {
+        int i4 = lane + 32 * j;
+        if (i4 < D4) {
+          float4 o;
+          o.x = rstd * (g[j].x - c1 - xh[j].x * c2);
+          o.y = rstd * (g[j].y - c1 - xh[j].y * c2);
+          o.z = rstd * (g[j].z - c1 - xh[j].z * c2);
+          o.w = rstd * (g[j].w - c1 - xh[j].w * c2);
+          if (d.accumulate_dx) {
+            float4 p = load4<TDX>(dx, i4);
+            o.x += p.x; o.y += p.y; o.z += p.z; o.w += p.w;
+          }
+          store4<TDX>(dx, i4, o);
+          if (d.dx_copy_bf16) store4<bf16>((bf16*)d.dx_copy_bf16 + row * d.D, i4, o);
+        }
+      }
+    }
+  }
+  if (!d.dgamma) return;  // uniform across the block
+  // reduce the 8 warps' partial dgamma/dbeta through smem, then one atomic per column per block
+#pragma unroll
+  for (int pass = 0; pass < 2; ++pass) {
+#pragma unroll
+    for (int j = 0; j < NV; ++j) {
+      __syncthreads();
+      float4 v = pass == 0 ? dg[j] : db[j];
+      red[warp][lane * 4 + 0] = v.x;
+      red[warp][lane * 4 + 1] = v.y;
+      red[warp][lane * 4 + 2] = v.z;
+      red[warp][lane * 4 + 3] = v.w;
+      __syncthreads();
+      if (threadIdx.x < 128) {
+        float s = 0.f;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) s += red[w][threadIdx.x];
+        int col = (threadIdx.x >> 2) * 4 + 128 * j + (threadIdx.x & 3);
+        if (col < d.D) atomicAdd((pass == 0 ? d.dgamma : d.dbeta) + col, s);
+      }
+    }
+  }
+}
+
+template <typename TX, typename TY>
+int launch_fwd(const sc_ln_desc& d, cudaStream_t st) {
+  const int nv = ceil_div(d.D, 128);
+  const int grid = ceil_div(d.rows, 8);
+#define SC_LN_CASE(NV_) ln_fwd_kernel<TX, TY, NV_><<<grid, 256, 0, st>>>(d)
+  switch (nv) {
+    case 1: SC_LN_CASE(1); break;
+    case 2: SC_LN_CASE(2); break;
+    case 3: SC_LN_CASE(3); break;
+    case 4: SC_LN_CASE(4); break;
+    case 5: case 6: SC_LN_CASE(6); break;
+    case 7: case 8: SC_LN_CASE(8); break;
+    default: sc_set_error("sc_layernorm_fwd: D=%d > 1024 unsupported", d.D); return SC_ERR_UNSUPPORTED;
+  }
+#undef SC_LN_CASE
+  SC_LAUNCH_CHECK();
+  return SC_OK;
+}
+
+template <typename TDY, typename TX, typename TDX>
+int launch_bwd(const sc_ln_bwd_desc& d, cudaStream_t st) {
+  const int nv = ceil_div(d.D, 128);
+  long g = ceil_div(d.rows, 8);
+  const int grid = (int)(g < 4L * sc_num_sms() ? g : 4L * sc_num_sms());
+#define SC_LN_CASE(NV_) ln_bwd_kernel<TDY, TX, TDX, NV_><<<grid, 256, 0, st>>>(d)
+  switch (nv) {
+    case 1: SC_LN_CASE(1); break;
+    case 2: SC_LN_CASE(2); break;
+    case 3: SC_LN_CASE(3); break;
+    case 4: SC_LN_CASE(4); break;
+    case 5: case 6: SC_LN_CASE(6); break;
+    case 7: case 8: SC_LN_CASE(8); break;
+    default: sc_set_error("sc_layernorm_bwd: D=%d > 1024 unsupported", d.D); return SC_ERR_UNSUPPORTED;
+  }
+#undef SC_LN_CASE
+  SC_LAUNCH_CHECK();
+  return SC_OK;
+}
+
+}  // namespace
+
+extern void sc_count_launch(int n);
+
+extern "C" int sc_layernorm_fwd(const sc_ln_desc* d, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  SC_CHECK_ARG(d && d->x && d->y && d->gamma && d->beta, "sc_layernorm_fwd: null pointer");
+  SC_CHECK_ARG(d->D % 4 == 0 && d->D > 0, "sc_layernorm_fwd: D=%d must be a multiple of 4", d->D);
+  if (d->rows <= 0) return SC_OK;
+  sc_count_launch(1);
+  if (d->x_dtype == SC_F32 && d->y_dtype == SC_F32) return launch_fwd<float, float>(*d, st);
+  if (d->x_dtype == SC_F32 && d->y_dtype == SC_BF16) return launch_fwd<float, bf16>(*d, st);
+  if (d->x_dtype == SC_BF16 && d->y_dtype == SC_BF16) return launch_fwd<bf16, bf16>(*d, st);
+  if (d->x_dtype == SC_BF16 && d->y_dtype == SC_F32) return launch_fwd<bf16, float>(*d, st);
+  sc_set_error("sc_layernorm_fwd: bad dtypes");
+  return SC_ERR_INVALID;
+}
+
+extern "C" int sc_layernorm_bwd(const sc_ln_bwd_desc* d, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  SC_CHECK_ARG(d && d->x && d->dy && d->gamma && d->mean && d->rstd, "sc_layernorm_bwd: null pointer");
+  SC_CHECK_ARG(d->D % 4 == 0 && d->D > 0, "sc_layernorm_bwd: D=%d must be a multiple of 4", d->D);
+  SC_CHECK_ARG((d->dgamma == nullptr) == (d->dbeta == nullptr), "sc_layernorm_bwd: dgamma/dbeta must come together");
+  if (d->rows <= 0) return SC_OK;
+  sc_count_launch(1);
+  const int key = d->dy_dtype * 4 + d->x_dtype * 2 + d->dx_dtype;
+  switch (key) {
+    case 0: return launch_bwd<float, float, float>(*d, st);
+    case 1: return launch_bwd<float, float, bf16>(*d, st);
+    case 2: return launch_bwd<float, bf16, float>(*d, st);
+    case 3: return launch_bwd<float, bf16, bf16>(*d, st);
+    case 4: return launch_bwd<bf16, float, float>(*d, st);
+    case 5: return launch_bwd<bf16, float, bf16>(*d, st);
+    case 6: return launch_bwd<bf16, bf16, float>(*d, st);
+    case 7: return launch_bwd<bf16, bf16, bf16>(*d, st);
+  }
+  sc_set_error("sc_layernorm_bwd: bad dtypes");
+  return SC_ERR_INVALID;
+}
