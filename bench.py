@@ -1,0 +1,263 @@
+"""bench.py -- image-text pairs/s, forward+backward, of the SegCLIP hot path on N B200s.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--batch B] [--heads]
+
+Own arm : the drop-in SegCLIP module (segclip_b200) in bf16, ViT-B/16 + text-77, per-GPU batch 256
+          (BASELINE.json configs[1]); weak scaling for N > 1 (one process per GPU under torchrun).
+          `value`   = device-timed (CUDA events) pairs/s with the batch already resident in HBM;
+          `e2e`     = the same metric through the public module API with HOST (pinned) input buffers,
+                      H2D copies of ids/image and a D2H read of the loss inside the timed region.
+Reference arm (--impl reference): the CPU oracle restatement of the reference's own PyTorch path
+          (oracle/segclip_oracle.py; the reference itself cannot travel to the GPU box), fp32, all host
+          threads, on a bounded sample (batch 16) of the same workload.
+One JSON line on stdout (rank 0).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+GF_PER_PAIR = {False: 110.0, True: 144.4}      # algorithmic GEMM FLOPs, fwd+bwd = 3x fwd
+METRIC = "image-text pairs/sec (224^2, seq77) fwd+bwd"
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        p = json.load(open(path))
+        return dict(tflops=p["bf16_tflops_sustained"], tflops_burst=p["bf16_tflops"], hbm=p["hbm_gbs"], src="measured")
+    return dict(tflops=1400.0, tflops_burst=1590.0, hbm=6650.0, src="fallback")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return None
+        self.proc.terminate()
+        sm = sorted(int(float(r[1])) for r in self.rows if len(r) >= 8)
+        if not sm:
+            return None
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({n for r in self.rows if len(r) >= 8 for n, v in zip(names, r[4:8]) if v.lower().startswith("active")})
+        return dict(sm_mhz=sm[len(sm) // 2], sm_max_mhz=int(float(self.rows[0][2])), reasons=reasons, samples=len(sm))
+
+
+def synthetic_batch(cfg, B, seed, rank, heads):
+    """SURVEY 8(d) generator (same as the oracle's make_batch, but vectorised for large B)."""
+    g = torch.Generator().manual_seed(seed + rank)
+    T, V, L = cfg["context"], cfg["vocab"], cfg["grid"] ** 2
+    res = cfg["patch"] * cfg["grid"]
+    image = torch.randn(B, 1, 3, res, res, generator=g)
+    n = torch.randint(5, T - 1, (B,), generator=g)
+    ids = torch.randint(1, V - 2, (B, T), generator=g)
+    pos = torch.arange(T).unsqueeze(0)
+    ids = torch.where(pos <= n.unsqueeze(1), ids, torch.zeros_like(ids))
+    ids[:, 0] = V - 2
+    ids[torch.arange(B), n + 1] = V - 1
+    ids = ids.view(B, 1, T)
+    seg = torch.randint(0, 6, (B, 1, cfg["grid"], cfg["grid"]), generator=g)
+    return dict(input_ids=ids, attention_mask=(ids != 0).long(), image=image, image_seg=seg)
+
+
+def run_reference(args):
+    """CPU arm: oracle port of the reference's PyTorch path, fp32, all host threads."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import segclip_oracle as so
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    cfg = so.vit_b16_config(use_mae=args.heads, use_kl=args.heads)
+    Bc = args.cpu_batch
+    params = so.init_params(cfg, seed=0)
+    frozen = ("vis_mae_decoder.decoder_pos_embed",)
+    batch, noise = so.make_batch(cfg, Bc, seed=0)
+    times = []
+    for i in range(args.warmup + args.steps):
+        t0 = time.perf_counter()
+        so.loss_and_grads(params, batch, noise, cfg, "torch18_flat", frozen=frozen)
+        dt = time.perf_counter() - t0
+        if i >= args.warmup:
+            times.append(dt)
+    ms = 1e3 * sum(times) / len(times)
+    v = Bc / (ms / 1e3)
+    sample = "batch %d of the same synthetic workload, fp32, %d steps after %d warm-up" % (Bc, args.steps, args.warmup)
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": v, "unit": "pairs/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload_name(args), "cpu_batch": Bc},
+        "cpu_baseline": {"value": v, "unit": "pairs/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": v, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+
+
+def workload_name(args):
+    return "ViT-B/16 SegCLIP full fwd+bwd, per-GPU batch %d, %s, bf16 (BASELINE configs[1])" % (
+        args.batch, "contrastive + MAE-recon + superpixel-KL" if args.heads else "contrastive only")
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200")
+    ap.add_argument("--batch", type=int, default=256, help="per-GPU batch")
+    ap.add_argument("--heads", action="store_true", help="enable MAE-reconstruction + superpixel-KL heads (config 4)")
+    ap.add_argument("--cpu-batch", type=int, default=16)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--precision", default="bf16")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl != "reference" else args.warmup
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch.distributed as dist
+    from oracle.ref_harness import fake_clip_state_dict          # shapes only (test/bench infrastructure)
+    from oracle import segclip_oracle as so
+    from segclip_b200 import _lib
+    from segclip_b200.modeling import SegCLIP
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    assert world == args.gpus, "launch with torchrun --nproc-per-node %d" % args.gpus
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    cfg = so.vit_b16_config(use_mae=args.heads, use_kl=args.heads)
+    tc = argparse.Namespace(local_rank=local, rank=rank, world_size=world, first_stage_layer=10,
+                            use_vision_mae_recon=args.heads, use_seglabel=args.heads, precision=args.precision)
+    torch.manual_seed(0)
+    model = SegCLIP(fake_clip_state_dict(cfg), tc).to(dev).train()
+    net = model
+    if world > 1:
+        from segclip_b200.p2p import EmbeddingExchange
+        model.attach_exchange(EmbeddingExchange(dist.group.WORLD, dev))
+        net = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local], find_unused_parameters=False,
+                                                        gradient_as_bucket_view=True)
+    B = args.batch
+    host = synthetic_batch(cfg, B, 0, rank, args.heads)
+    pinned = {k: v.pin_memory() for k, v in host.items()}
+    resident = {k: v.to(dev) for k, v in host.items()}
+
+    def step(src, read_loss):
+        net.zero_grad(set_to_none=True)
+        loss = net(src["input_ids"], None, None, src["image"], image_seg=src["image_seg"] if args.heads else None)
+        loss.backward()
+        return float(loss) if read_loss else loss
+
+    def timed(src, read_loss, steps):
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            step(src, read_loss)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / steps
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t)
+        return ms
+
+    for _ in range(args.warmup):
+        step(resident, False)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    l0 = _lib.launch_count()
+    ms = timed(resident, False, args.steps)
+    launches = (_lib.launch_count() - l0) // args.steps
+    clocks = sampler.stop() if rank == 0 else None
+    step(pinned, True)
+    ms_e2e = timed(pinned, True, args.steps)
+
+    # dominant kernel (tcgen05 GEMM): achieved TFLOP/s over all its launches of one step, CUDA events
+    gemm = model._engine.profile_gemm(B) if rank == 0 else None
+
+    if rank != 0:
+        if world > 1:
+            dist.barrier()
+        return
+    pk = peaks()
+    value = B * world / (ms / 1e3)
+    gf = GF_PER_PAIR[args.heads]
+    out = {
+        "metric": METRIC, "value": value, "unit": "pairs/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
+        "data": "synthetic",
+        "config": {"workload": workload_name(args), "per_gpu_batch": B, "global_batch": B * world,
+                   "parallelism": "dp%d" % world, "l2": "per-step working set (GBs of activations) exceeds the 126 MB L2"},
+        "e2e": {"value": B * world / (ms_e2e / 1e3), "unit": "pairs/s",
+                "h2d_bytes_per_step": int(host["input_ids"].numel() * 8 + host["image"].numel() * 4 +
+                                          (host["image_seg"].numel() * 8 if args.heads else 0)),
+                "d2h_bytes_per_step": 4},
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+        "step_tensor_frac": {"achieved_tflops_per_gpu": value / world * gf / 1e3, "peak": pk["tflops"],
+                             "frac": value / world * gf / 1e3 / pk["tflops"], "flops_per_pair_gf": gf},
+        "roofline": {"bound": "tensor", "achieved": gemm["tflops"], "peak": pk["tflops"], "unit": "TFLOP/s",
+                     "frac": gemm["tflops"] / pk["tflops"], "traffic": None, "kernel": "gemm_tc_kernel (tcgen05)",
+                     "launches_per_step": gemm["launches"], "share_of_step": gemm["ms"] / ms, "peak_source": pk["src"]},
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        out["cpu_baseline"] = cpu_baseline(so, args)
+    print(json.dumps(out))
+    if world > 1:
+        dist.barrier()
+
+
+def cpu_baseline(so, args):
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    cfg = so.vit_b16_config(use_mae=args.heads, use_kl=args.heads)
+    Bc = args.cpu_batch
+    params = so.init_params(cfg, seed=0)
+    batch, noise = so.make_batch(cfg, Bc, seed=0)
+    best = None
+    for i in range(3):
+        t0 = time.perf_counter()
+        so.loss_and_grads(params, batch, noise, cfg, "torch18_flat", frozen=("vis_mae_decoder.decoder_pos_embed",))
+        dt = time.perf_counter() - t0
+        if i > 0:
+            best = dt if best is None else min(best, dt)
+    return {"value": Bc / best, "unit": "pairs/s", "cores": cores, "kind": "port",
+            "sample": "oracle port (fp32 PyTorch CPU), batch %d, best of 2 after 1 warm-up" % Bc}
+
+
+if __name__ == "__main__":
+    main()

@@ -28,6 +28,27 @@ int sc_num_sms() {
   return n;
 }
 
+// Entry points may be called from a thread that has not touched the CUDA runtime yet (autograd's
+// backward worker).  Driver-API calls (cuTensorMapEncodeTiled) need the primary context bound to the
+// calling thread, and the thread's current device must be the stream's.
+int sc_enter(cudaStream_t st) {
+  static thread_local bool bound = false;
+  int cur = -1;
+  SC_CUDA(cudaGetDevice(&cur));
+  if (st != nullptr && st != cudaStreamLegacy && st != cudaStreamPerThread) {
+    int dev = cur;
+    if (cudaStreamGetDevice(st, &dev) == cudaSuccess && dev != cur) {
+      SC_CUDA(cudaSetDevice(dev));
+      bound = false;
+    }
+  }
+  if (!bound) {
+    SC_CUDA(cudaFree(0));
+    bound = true;
+  }
+  return SC_OK;
+}
+
 int sc_gemm_tc(const sc_gemm_desc* d, cudaStream_t st);
 int sc_gemm_simt(const sc_gemm_desc* d, cudaStream_t st);
 
@@ -42,6 +63,10 @@ int sc_gemm(const sc_gemm_desc* d, void* stream) {
   SC_CHECK_ARG(d && d->A && d->B && d->C, "sc_gemm: null operand");
   SC_CHECK_ARG(d->M > 0 && d->N > 0 && d->K > 0, "sc_gemm: bad shape %d %d %d", d->M, d->N, d->K);
   SC_CHECK_ARG(!(d->accumulate && d->c_dtype != SC_F32), "sc_gemm: accumulate needs fp32 C");
+  {
+    int rc = sc_enter(st);
+    if (rc) return rc;
+  }
   if (d->in_dtype == SC_BF16 && !d->force_simt) return sc_gemm_tc(d, st);
   SC_CHECK_ARG(d->in_dtype == SC_F32 || d->in_dtype == SC_BF16, "sc_gemm: bad in_dtype %d", d->in_dtype);
   return sc_gemm_simt(d, st);

@@ -597,6 +597,40 @@ class Engine:
             op(st)
         return self.gflat
 
+    def profile_gemm(self, B):
+        """One extra instrumented step: CUDA events around every tensor-core GEMM launch (on the launching
+        stream).  Returns total algorithmic FLOPs / total device time of the dominant kernel."""
+        pl = self.plan(B)
+        st = L.stream()
+        recs = []
+
+        def run(op):
+            if isinstance(op, str):
+                self._collective(op, pl)
+                return
+            if isinstance(op, tuple):
+                op = op[0]
+            d = op.keep[0] if op.name == "sc_gemm" else None
+            if d is not None and d.in_dtype == L.BF16:
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                op(st)
+                e1.record()
+                recs.append((e0, e1, 2.0 * d.M * d.N * d.K))
+            else:
+                op(st)
+
+        torch._foreach_zero_(pl.zero)
+        self.gflat.zero_()
+        for op in pl.fwd:
+            run(op)
+        for op in pl.bwd:
+            run(op)
+        torch.cuda.synchronize()
+        ms = sum(a.elapsed_time(b) for a, b, _ in recs)
+        fl = sum(f for _, _, f in recs)
+        return dict(ms=ms, launches=len(recs), tflops=fl / ms / 1e9 if ms > 0 else 0.0, flops=fl)
+
     def _collective(self, what, pl):
         if self.world == 1:
             if what == "gather_lse":
