@@ -148,6 +148,9 @@ int sc_layernorm_bwd(const sc_ln_bwd_desc* d, void* stream);
  * buffers and both centre-cross-attention K/V layouts ("torch18_flat" k_bs = row,
  * k_rs = B rows; "per_sample" k_bs = Lk rows, k_rs = row) are expressed without copies.
  * lse[b,h,i] = log sum_j exp(s_ij) is saved for the backward pass.
+ * bf16 problems with head dim 32/48/64 and 16 <= L <= 1024 run flash-style on the tensor cores
+ * (mma.sync m16n8k16, no [L,L] matrix in HBM); everything else (fp32 parity mode, the 8-query centre
+ * cross-attention, tiny L) runs on an exact fp32 kernel.
  */
 typedef struct {
   int32_t B, H, Lq, Lk, hd;
@@ -163,6 +166,7 @@ typedef struct {
   void* o;
   int64_t o_bs, o_rs;
   float* lse; /* [B, H, Lq] */
+  int32_t force_generic; /* debugging: skip the tensor-core kernels */
 } sc_attn_desc;
 int sc_attention_fwd(const sc_attn_desc* a, void* stream);
 
@@ -172,6 +176,7 @@ typedef struct {
   void* d_q;        /* strides of q, k, v respectively */
   void* d_k;
   void* d_v;
+  float* delta_ws; /* fp32 scratch [B, H, Lq] (rowsum(dO o O)); required by the tensor-core kernels */
 } sc_attn_bwd_desc;
 int sc_attention_bwd(const sc_attn_bwd_desc* g, void* stream);
 

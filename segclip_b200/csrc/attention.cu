@@ -241,11 +241,15 @@ int set_smem(K kern, size_t bytes, const char* who) {
 }  // namespace
 
 extern void sc_count_launch(int n);
+bool sc_attn_mma_supported(const sc_attn_desc* a);
+int sc_attention_fwd_mma(const sc_attn_desc* a, cudaStream_t st);
+int sc_attention_bwd_mma(const sc_attn_bwd_desc* g, float* delta, cudaStream_t st);
 
 extern "C" int sc_attention_fwd(const sc_attn_desc* a, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
   int rc = check_desc(a, "sc_attention_fwd");
   if (rc) return rc;
+  if (!a->force_generic && a->lse && sc_attn_mma_supported(a)) return sc_attention_fwd_mma(a, st);
   const size_t smem = sizeof(float) * ((size_t)2 * a->Lk * (a->hd + 1) + (size_t)ATT_WARPS * a->Lk + ATT_WARPS * 64);
   dim3 grid(a->H, a->B);
   sc_count_launch(1);
@@ -266,6 +270,7 @@ extern "C" int sc_attention_bwd(const sc_attn_bwd_desc* g, void* stream) {
   int rc = check_desc(a, "sc_attention_bwd");
   if (rc) return rc;
   SC_CHECK_ARG(g->d_o && g->d_q && g->d_k && g->d_v && a->lse, "sc_attention_bwd: null pointer");
+  if (!a->force_generic && g->delta_ws && sc_attn_mma_supported(a)) return sc_attention_bwd_mma(g, g->delta_ws, st);
   const size_t smem_q = sizeof(float) * ((size_t)2 * a->Lk * (a->hd + 1) + (size_t)ATT_WARPS * a->Lk + 2 * ATT_WARPS * 64);
   const size_t smem_kv = sizeof(float) * ((size_t)2 * a->Lq * (a->hd + 1) + 2 * (size_t)a->Lq +
                                           2 * (size_t)ATT_WARPS * a->Lq + 2 * ATT_WARPS * 64);

@@ -274,7 +274,7 @@ class Engine:
             grp_mlp = mlp(x_mid, x_out, dx, dxT, pre, nm, tag, eps, act)
             d_att, dqkv, d_ln = sbuf("d_att", (M, D), T), sbuf("dqkv", (M, 3 * D), T), sbuf("d_ln", (M, D), T)
             grp = linear_bwd(dxT, att, pre + nm["wo"], pre + nm["bo"], dx=d_att)
-            grp.append(ops.attention_bwd_op(ad, d_att, dqkv, dqkv[:, D:], dqkv[:, 2 * D:]))
+            grp.append(ops.attention_bwd_op(ad, d_att, dqkv, dqkv[:, D:], dqkv[:, 2 * D:], sbuf("att_delta", (Bn, H, Lseq), f32)))
             grp += linear_bwd(dqkv, h1, pre + nm["wqkv"], pre + nm["bqkv"], dx=d_ln)
             grp.append(ln_bwd(d_ln, x_in, st1, pre + nm["ln1"], dx, True, dxT))
             pl.b(grp)          # executed after the MLP group (groups run in reverse order)

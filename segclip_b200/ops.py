@@ -121,7 +121,7 @@ def layernorm_bwd_op(dy, x, mean, rstd, gamma, dx=None, accumulate_dx=False, dx_
     return Op("sc_layernorm_bwd", (C.byref(d),), (d, dy, x, mean, rstd, gamma, dx, dx_copy, dgamma, dbeta))
 
 
-def attn_desc(q, k, v, o, lse, B, H, Lq, Lk, hd, q_str, k_str, v_str, o_str, causal=False):
+def attn_desc(q, k, v, o, lse, B, H, Lq, Lk, hd, q_str, k_str, v_str, o_str, causal=False, force_generic=False):
     """q/k/v/o are base tensors (already offset to their first element); *_str = (batch stride, row stride)."""
     a = L.AttnDesc()
     a.B, a.H, a.Lq, a.Lk, a.hd = B, H, Lq, Lk, hd
@@ -133,6 +133,7 @@ def attn_desc(q, k, v, o, lse, B, H, Lq, Lk, hd, q_str, k_str, v_str, o_str, cau
     a.v, (a.v_bs, a.v_rs) = v.data_ptr(), v_str
     a.o, (a.o_bs, a.o_rs) = o.data_ptr(), o_str
     a.lse = lse.data_ptr()
+    a.force_generic = int(force_generic)
     return a
 
 
@@ -140,11 +141,14 @@ def attention_op(a, keep=()):
     return Op("sc_attention_fwd", (C.byref(a),), (a, keep))
 
 
-def attention_bwd_op(a, d_o, d_q, d_k, d_v, keep=()):
+def attention_bwd_op(a, d_o, d_q, d_k, d_v, delta_ws=None, keep=()):
     g = L.AttnBwdDesc()
     g.fwd = a
     g.d_o, g.d_q, g.d_k, g.d_v = d_o.data_ptr(), d_q.data_ptr(), d_k.data_ptr(), d_v.data_ptr()
-    return Op("sc_attention_bwd", (C.byref(g),), (g, d_o, d_q, d_k, d_v, keep))
+    if delta_ws is not None:
+        assert delta_ws.dtype == torch.float32 and delta_ws.numel() >= a.B * a.H * a.Lq
+        g.delta_ws = delta_ws.data_ptr()
+    return Op("sc_attention_bwd", (C.byref(g),), (g, d_o, d_q, d_k, d_v, delta_ws, keep))
 
 
 def act_bwd_op(dy, pre, dx, act):

@@ -1,0 +1,82 @@
+"""sc_attention_fwd / sc_attention_bwd (tensor-core flash kernels and the generic fp32 kernels) against a
+plain fp32 torch reference of softmax(q k^T / sqrt(hd) + mask) v and its autograd gradients."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _ref(q, k, v, do, causal):
+    q, k, v = (t.float().detach().requires_grad_(True) for t in (q, k, v))
+    s = torch.einsum("bihd,bjhd->bhij", q, k) * q.shape[-1] ** -0.5
+    if causal:
+        L = s.shape[-1]
+        s = s + torch.full((L, L), float("-inf"), device=s.device).triu_(1)
+    p = torch.softmax(s, -1)
+    o = torch.einsum("bhij,bjhd->bihd", p, v)
+    o.backward(do.float())
+    return o.detach(), torch.logsumexp(s, -1).detach(), q.grad, k.grad, v.grad
+
+
+def _run(B, H, L, hd, dtype, causal=False, force_generic=False, seed=0):
+    from segclip_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    D = H * hd
+    qkv = (torch.randn(B * L, 3 * D, device="cuda", generator=g) * 1.5).to(dtype)
+    do = torch.randn(B * L, D, device="cuda", generator=g).to(dtype)
+    o = torch.full((B * L, D), float("nan"), device="cuda", dtype=dtype)
+    lse = torch.empty(B, H, L, device="cuda")
+    st = (L * 3 * D, 3 * D)
+    a = ops.attn_desc(qkv, qkv[:, D:], qkv[:, 2 * D:], o, lse, B, H, L, L, hd, st, st, st, (L * D, D), causal, force_generic)
+    ops.attention_op(a)()
+    dqkv = torch.full_like(qkv, float("nan"))
+    delta = torch.empty(B, H, L, device="cuda")
+    ops.attention_bwd_op(a, do, dqkv, dqkv[:, D:], dqkv[:, 2 * D:], delta)()
+    torch.cuda.synchronize()
+    v4 = qkv.view(B, L, 3, H, hd)
+    ro, rl, rq, rk, rv = _ref(v4[:, :, 0], v4[:, :, 1], v4[:, :, 2], do.view(B, L, H, hd), causal)
+    tol = 2e-5 if dtype == torch.float32 else 2e-2
+    def rel(x, y):
+        return float((x.float() - y).abs().max() / (y.abs().max() + 1e-9))
+    assert rel(o.view(B, L, H, hd), ro) < tol
+    assert float((lse - rl).abs().max()) < (1e-4 if dtype == torch.float32 else 2e-2)
+    d4 = dqkv.view(B, L, 3, H, hd)
+    assert rel(d4[:, :, 0], rq) < tol, rel(d4[:, :, 0], rq)
+    assert rel(d4[:, :, 1], rk) < tol, rel(d4[:, :, 1], rk)
+    assert rel(d4[:, :, 2], rv) < tol, rel(d4[:, :, 2], rv)
+
+
+@pytest.mark.parametrize("B,H,L,hd,causal", [(3, 12, 196, 64, False), (2, 8, 77, 64, True), (2, 8, 197, 48, False),
+                                             (2, 12, 48, 64, False), (1, 2, 16, 32, False), (2, 4, 130, 64, True),
+                                             (1, 2, 577, 64, False)])
+def test_tensor_core_attention(B, H, L, hd, causal):
+    _run(B, H, L, hd, torch.bfloat16, causal)
+
+
+@pytest.mark.parametrize("B,H,L,hd,causal", [(2, 3, 50, 64, False), (2, 2, 33, 48, True), (2, 2, 8, 8, False)])
+def test_generic_fp32_attention(B, H, L, hd, causal):
+    _run(B, H, L, hd, torch.float32, causal)
+
+
+def test_generic_bf16_matches_too():
+    _run(2, 12, 196, 64, torch.bfloat16, False, force_generic=True)
+
+
+def test_cross_attention_flat_kv_layout():
+    """K/V addressed with the torch-1.8 flat re-interpretation: slot b' key s = flat row s*B+b'."""
+    from segclip_b200 import ops
+    torch.manual_seed(0)
+    B, H, hd, G, S = 3, 2, 64, 8, 24
+    D = H * hd
+    q = torch.randn(B * G, D, device="cuda")
+    kv = torch.randn(B * S, 2 * D, device="cuda")
+    o = torch.empty(B * G, D, device="cuda")
+    lse = torch.empty(B, H, G, device="cuda")
+    a = ops.attn_desc(q, kv, kv[:, D:], o, lse, B, H, G, S, hd, (G * D, D), (2 * D, B * 2 * D), (2 * D, B * 2 * D), (G * D, D))
+    ops.attention_op(a)()
+    torch.cuda.synchronize()
+    kf = kv[:, :D].reshape(S, B, D).transpose(0, 1)       # [B, S, D] as torch 1.8 saw it
+    vf = kv[:, D:].reshape(S, B, D).transpose(0, 1)
+    s = torch.einsum("bihd,bjhd->bhij", q.view(B, G, H, hd), kf.reshape(B, S, H, hd)) * hd ** -0.5
+    ref = torch.einsum("bhij,bjhd->bihd", torch.softmax(s, -1), vf.reshape(B, S, H, hd)).reshape(B * G, D)
+    assert float((o - ref).abs().max()) < 1e-4
