@@ -53,7 +53,7 @@ long long sc_launch_count(void);
  *   acc[m,n] = sum_k A(m,k) * B(n,k)
  *   v        = alpha*acc + bias[n] + rowbias[ridx(m), n]
  *   if C2: C2[m,n] = v                       (pre-activation copy, saved for backward)
- *   v        = act(v) + residual[m,n]
+ *   v        = act(v) * act'(mul_aux[m,n]) + residual[m,n]     (act' term only if mul_aux)
  *   C[m,n]   = v   (or C[m,n] += v when accumulate; fp32 C only; atomic when split_k > 1)
  *
  * A(m,k) = A[m*lda + k] (trans_a = 0, "K-major") or A[k*lda + m] (trans_a = 1, "MN-major");
@@ -90,6 +90,9 @@ typedef struct {
   int32_t accumulate;
   int32_t split_k;       /* 0/1 = none; >1 requires accumulate into fp32 C (atomic adds) */
   int32_t force_simt;    /* debugging / cross-checking: run the bf16 problem on the FMA kernel */
+  const void* mul_aux;   /* optional [M,N] (leading dim ldc): v *= act'(mul_aux) after act -- fused QuickGELU/GELU backward */
+  int32_t mul_aux_dtype;
+  int32_t mul_aux_act;
 } sc_gemm_desc;
 
 int sc_gemm(const sc_gemm_desc* d, void* stream);

@@ -373,7 +373,7 @@ extern void sc_count_launch(int n);
 
 // Whether the tensor-core kernels cover this problem (otherwise the generic fp32 kernels run).
 bool sc_attn_mma_supported(const sc_attn_desc* a) {
-  return a->dtype == SC_BF16 && (a->hd == 64 || a->hd == 48 || a->hd == 32) && a->Lq >= 16 && a->Lk >= 16 &&
+  return a->dtype == SC_BF16 && (a->hd == 64 || a->hd == 48 || a->hd == 32) && a->Lq >= 1 && a->Lk >= 16 &&
          a->Lq <= 1024 && a->Lk <= 1024 && a->B <= 65535 && a->H <= 65535 && aligned_for_mma(a);
 }
 

@@ -21,6 +21,9 @@ struct EpiParams {
   int c2_dtype;
   int accumulate;
   int atomic;  // accumulate with atomics (split-K)
+  const void* mul_aux;  // optional: v *= act'(mul_aux[m,n]) (fused activation backward), leading dim ldc
+  int mul_aux_dtype;
+  int mul_aux_act;
 };
 
 static inline EpiParams make_epi(const sc_gemm_desc* d) {
@@ -43,6 +46,9 @@ static inline EpiParams make_epi(const sc_gemm_desc* d) {
   p.c2_dtype = d->c2_dtype;
   p.accumulate = d->accumulate;
   p.atomic = d->split_k > 1;
+  p.mul_aux = d->mul_aux;
+  p.mul_aux_dtype = d->mul_aux_dtype;
+  p.mul_aux_act = d->mul_aux_act;
   return p;
 }
 
@@ -57,6 +63,7 @@ SC_DEVINL void epi_store_scalar(const EpiParams& p, int m, int n, float acc) {
   long off = (long)m * p.ldc + n;
   if (p.C2) st_any(p.C2, off, p.c2_dtype, v);
   v = act_fwd(v, p.act);
+  if (p.mul_aux) v *= act_grad(ld_any(p.mul_aux, off, p.mul_aux_dtype), p.mul_aux_act);
   if (p.residual) v += p.residual[(long)m * p.ldr + n];
   if (p.atomic) {
     atomicAdd((float*)p.C + off, v);
@@ -67,66 +74,59 @@ SC_DEVINL void epi_store_scalar(const EpiParams& p, int m, int n, float acc) {
   }
 }
 
-// 8 consecutive columns of one row, 16B-aligned everywhere (tcgen05 kernel).
-SC_DEVINL void st8(void* base, long off, int dtype, const float* v) {
+// 4 consecutive columns of one row, 16-byte aligned everywhere (tcgen05 kernel, after the smem transpose:
+// the 8 lanes of a quarter-warp cover 32 consecutive columns of the same row -> full-line global accesses).
+SC_DEVINL void st4(void* base, long off, int dtype, const float4& v) {
   if (dtype == SC_F32) {
-    float4* p = (float4*)((float*)base + off);
-    p[0] = make_float4(v[0], v[1], v[2], v[3]);
-    p[1] = make_float4(v[4], v[5], v[6], v[7]);
+    *(float4*)((float*)base + off) = v;
   } else {
-    __nv_bfloat162 a = __floats2bfloat162_rn(v[0], v[1]);
-    __nv_bfloat162 b = __floats2bfloat162_rn(v[2], v[3]);
-    __nv_bfloat162 c = __floats2bfloat162_rn(v[4], v[5]);
-    __nv_bfloat162 d = __floats2bfloat162_rn(v[6], v[7]);
-    uint4 u;
+    __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y), b = __floats2bfloat162_rn(v.z, v.w);
+    uint2 u;
     u.x = *(uint32_t*)&a;
     u.y = *(uint32_t*)&b;
-    u.z = *(uint32_t*)&c;
-    u.w = *(uint32_t*)&d;
-    *(uint4*)((bf16*)base + off) = u;
+    *(uint2*)((bf16*)base + off) = u;
   }
 }
+SC_DEVINL float4 ld4(const void* base, long off, int dtype) {
+  if (dtype == SC_F32) return *(const float4*)((const float*)base + off);
+  uint2 u = *(const uint2*)((const bf16*)base + off);
+  float2 a = __bfloat1622float2(*(__nv_bfloat162*)&u.x), b = __bfloat1622float2(*(__nv_bfloat162*)&u.y);
+  return make_float4(a.x, a.y, b.x, b.y);
+}
 
-SC_DEVINL void epi_store8(const EpiParams& p, int m, int n, float* v) {
-#pragma unroll
-  for (int i = 0; i < 8; ++i) v[i] *= p.alpha;
+SC_DEVINL void epi_store4(const EpiParams& p, int m, int n, float4 v) {
+  v.x *= p.alpha; v.y *= p.alpha; v.z *= p.alpha; v.w *= p.alpha;
   if (p.bias) {
-    float4 b0 = __ldg((const float4*)(p.bias + n));
-    float4 b1 = __ldg((const float4*)(p.bias + n + 4));
-    v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
-    v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
+    const float4 b = __ldg((const float4*)(p.bias + n));
+    v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
   }
   if (p.rowbias) {
-    int r = p.rowbias_idx ? p.rowbias_idx[m] : (m % p.rowbias_mod);
-    const float* rb = p.rowbias + (long)r * p.ld_rowbias + n;
-    float4 b0 = __ldg((const float4*)rb);
-    float4 b1 = __ldg((const float4*)(rb + 4));
-    v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
-    v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
+    const int r = p.rowbias_idx ? p.rowbias_idx[m] : (m % p.rowbias_mod);
+    const float4 b = __ldg((const float4*)(p.rowbias + (long)r * p.ld_rowbias + n));
+    v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
   }
-  long off = (long)m * p.ldc + n;
-  if (p.C2) st8(p.C2, off, p.c2_dtype, v);
+  const long off = (long)m * p.ldc + n;
+  if (p.C2) st4(p.C2, off, p.c2_dtype, v);
   if (p.act != SC_ACT_NONE) {
-#pragma unroll
-    for (int i = 0; i < 8; ++i) v[i] = act_fwd(v[i], p.act);
+    v.x = act_fwd(v.x, p.act); v.y = act_fwd(v.y, p.act); v.z = act_fwd(v.z, p.act); v.w = act_fwd(v.w, p.act);
+  }
+  if (p.mul_aux) {
+    const float4 a = ld4(p.mul_aux, off, p.mul_aux_dtype);
+    v.x *= act_grad(a.x, p.mul_aux_act); v.y *= act_grad(a.y, p.mul_aux_act);
+    v.z *= act_grad(a.z, p.mul_aux_act); v.w *= act_grad(a.w, p.mul_aux_act);
   }
   if (p.residual) {
-    const float* r = p.residual + (long)m * p.ldr + n;
-    float4 r0 = *(const float4*)r;
-    float4 r1 = *(const float4*)(r + 4);
-    v[0] += r0.x; v[1] += r0.y; v[2] += r0.z; v[3] += r0.w;
-    v[4] += r1.x; v[5] += r1.y; v[6] += r1.z; v[7] += r1.w;
+    const float4 r = *(const float4*)(p.residual + (long)m * p.ldr + n);
+    v.x += r.x; v.y += r.y; v.z += r.z; v.w += r.w;
   }
   if (p.atomic) {
     float* c = (float*)p.C + off;
-#pragma unroll
-    for (int i = 0; i < 8; ++i) atomicAdd(c + i, v[i]);
+    atomicAdd(c, v.x); atomicAdd(c + 1, v.y); atomicAdd(c + 2, v.z); atomicAdd(c + 3, v.w);
   } else if (p.accumulate) {
     float4* c = (float4*)((float*)p.C + off);
-    float4 c0 = c[0], c1 = c[1];
-    c[0] = make_float4(c0.x + v[0], c0.y + v[1], c0.z + v[2], c0.w + v[3]);
-    c[1] = make_float4(c1.x + v[4], c1.y + v[5], c1.z + v[6], c1.w + v[7]);
+    const float4 o = *c;
+    *c = make_float4(o.x + v.x, o.y + v.y, o.z + v.z, o.w + v.w);
   } else {
-    st8(p.C, off, p.c_dtype, v);
+    st4(p.C, off, p.c_dtype, v);
   }
 }

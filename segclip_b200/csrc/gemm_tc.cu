@@ -115,7 +115,7 @@ struct TileCfg {
   static constexpr int B_BYTES = BN * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int TMEM_COLS = 2 * BN;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/ + NUM_EPI_WARPS * 4096;
 };
 
 template <int BN, bool A_MN, bool B_MN>
@@ -133,6 +133,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint64_t* tmem_full = bars + 2 * Cfg::STAGES;
   uint64_t* tmem_empty = tmem_full + 2;
   uint32_t* tmem_slot = (uint32_t*)(tmem_empty + 2);
+  uint8_t* epi_stage = smem + Cfg::STAGES * Cfg::STAGE_BYTES + 256;   // 8 warps x 4 KB
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -237,27 +238,36 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // =============================== epilogue ===============================
     const int quarter = warp & 3;       // TMEM lane quarter this warp may access
     const int half = warp >> 2;         // column half of the tile
+    uint8_t* stage = epi_stage + warp * 4096;
     int it = 0;
     for (int item = blockIdx.x; item < num_items; item += gridDim.x, ++it) {
       const int nt = item % tiles_n;
       const int mt = (item / tiles_n) % tiles_m;
-      const int m = mt * BM + quarter * 32 + lane;
       const int nbase = nt * BN + half * (BN / 2);
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
       mbar_wait(&tmem_full[acc], acc_phase);
       tcgen05_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BN + half * (BN / 2);
+      const int mrow0 = mt * BM + quarter * 32;
 #pragma unroll 1
       for (int c = 0; c < BN / 2 / 32; ++c) {
         float v[32];
         tmem_ld32(taddr + c * 32, v);
-        if (m < ep.M) {
+        // transpose through the warp's private smem patch (32 rows x 128 B, 16-byte chunks XOR-swizzled by row)
+        // so that global loads/stores of the epilogue are full-line: 8 lanes cover 32 consecutive columns of a row.
+        __syncwarp();
 #pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            const int n = nbase + c * 32 + g * 8;
-            if (n < ep.N) epi_store8(ep, m, n, v + g * 8);
-          }
+        for (int j = 0; j < 8; ++j)
+          *(float4*)(stage + lane * 128 + ((j ^ (lane & 7)) << 4)) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+        __syncwarp();
+        const int n = nbase + c * 32 + (lane & 7) * 4;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int r = 4 * i + (lane >> 3);
+          const float4 x = *(const float4*)(stage + r * 128 + (((lane & 7) ^ (r & 7)) << 4));
+          const int m = mrow0 + r;
+          if (m < ep.M && n < ep.N) epi_store4(ep, m, n, x);
         }
       }
       tcgen05_fence_before();
@@ -386,7 +396,7 @@ int sc_gemm_tc(const sc_gemm_desc* d, cudaStream_t st) {
   if (!(d->lda % 8 == 0 && d->ldb % 8 == 0 && aligned16(d->A) && aligned16(d->B) && d->N % 8 == 0 &&
         d->ldc % 8 == 0 && aligned16(d->C) && (!d->C2 || aligned16(d->C2)) &&
         (!d->bias || aligned16(d->bias)) && (!d->residual || (aligned16(d->residual) && d->ldr % 4 == 0)) &&
-        (!d->rowbias || (aligned16(d->rowbias) && d->ld_rowbias % 4 == 0)))) {
+        (!d->rowbias || (aligned16(d->rowbias) && d->ld_rowbias % 4 == 0)) && (!d->mul_aux || aligned16(d->mul_aux)))) {
     sc_set_error("sc_gemm(bf16): operands must be 16-byte aligned with leading dimensions multiple of 8 "
                  "(M=%d N=%d K=%d lda=%lld ldb=%lld ldc=%lld)", d->M, d->N, d->K, (long long)d->lda,
                  (long long)d->ldb, (long long)d->ldc);

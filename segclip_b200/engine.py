@@ -211,7 +211,7 @@ class Engine:
         center_idx = torch.arange(G, device=dev, dtype=i32).repeat(B)
 
         # ---------------- generic layers
-        def linear_bwd(dy, x, wname, bname, dx=None, dx_acc=False, wslice=None, bslice=None):
+        def linear_bwd(dy, x, wname, bname, dx=None, dx_acc=False, wslice=None, bslice=None, mul_aux=None, mul_act=0):
             w = self.W(wname)
             gw = self.Gr(wname)
             gb = self.grads[bname] if bname else None
@@ -221,7 +221,7 @@ class Engine:
                 gb = gb[bslice]
             grp = []
             if dx is not None:
-                grp.append(ops.gemm_op(dy, w, dx, trans_b=True, accumulate=dx_acc))
+                grp.append(ops.gemm_op(dy, w, dx, trans_b=True, accumulate=dx_acc, mul_aux=mul_aux, mul_aux_act=mul_act))
             grp.append(ops.gemm_op(dy, x, gw, trans_a=True, trans_b=True, accumulate=True, split_k=-1))
             if gb is not None:
                 grp.append(ops.colsum_op(dy, gb))
@@ -248,8 +248,7 @@ class Engine:
             pl.f(ops.gemm_op(h2, self.W(pre + nm["w1"]), hact, bias=self.P(pre + nm["b1"]), act=act, C2=hpre))
             pl.f(ops.gemm_op(hact, self.W(pre + nm["w2"]), x_out, bias=self.P(pre + nm["b2"]), residual=x_mid))
             d_a, d_ln = sbuf("d_a", (M, Dh), T), sbuf("d_ln", (M, D), T)
-            grp = linear_bwd(dxT, hact, pre + nm["w2"], pre + nm["b2"], dx=d_a)
-            grp.append(ops.act_bwd_op(d_a, hpre, d_a, act))
+            grp = linear_bwd(dxT, hact, pre + nm["w2"], pre + nm["b2"], dx=d_a, mul_aux=hpre, mul_act=act)  # fused act'()
             grp += linear_bwd(d_a, h2, pre + nm["w1"], pre + nm["b1"], dx=d_ln)
             grp.append(ln_bwd(d_ln, x_mid, st2, pre + nm["ln2"], dx, True, dxT))
             return grp
@@ -366,8 +365,8 @@ class Engine:
             d_v, d_k = sbuf("d_v", (Mx, D), T), sbuf("d_k", (Mx, D), f32)
             d_kfeat, d_xin = sbuf("d_kfeat", (Mx, D), T), sbuf("d_xin", (Mx, D), f32)
             grp = [ops.act_bwd_op(d_sx, pre2, d_pre2, ops.ACT_QUICKGELU)]
-            grp += linear_bwd(d_pre2, a1, s + "proj_o.mlp.fc2.weight", s + "proj_o.mlp.fc2.bias", dx=d_a1)
-            grp.append(ops.act_bwd_op(d_a1, pre1, d_a1, ops.ACT_GELU_ERF))
+            grp += linear_bwd(d_pre2, a1, s + "proj_o.mlp.fc2.weight", s + "proj_o.mlp.fc2.bias", dx=d_a1, mul_aux=pre1,
+                              mul_act=ops.ACT_GELU_ERF)
             grp += linear_bwd(d_a1, hp, s + "proj_o.mlp.fc1.weight", s + "proj_o.mlp.fc1.bias", dx=d_h)
             grp.append(ln_bwd(d_h, ssum, st_po, s + "proj_o.ln", d_sum))
             grp.append(ops.assign_bwd_op(d_sum, agg, vfeat, idx, count, y_soft, d_hard_extra, qf, k, d_logits, d_v, d_k,

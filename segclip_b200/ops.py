@@ -34,7 +34,8 @@ def _p(t):
 
 
 def gemm_desc(A, B, C_, *, trans_a=False, trans_b=False, bias=None, rowbias=None, rowbias_idx=None, rowbias_mod=0,
-              act=ACT_NONE, residual=None, C2=None, accumulate=False, split_k=0, alpha=1.0, force_simt=False):
+              act=ACT_NONE, residual=None, C2=None, accumulate=False, split_k=0, alpha=1.0, force_simt=False,
+              mul_aux=None, mul_aux_act=ACT_NONE):
     """sc_gemm descriptor for C = epi(A B^T); see include/segclip_b200.h."""
     for t in (A, B, C_):
         _chk2d(t)
@@ -73,6 +74,10 @@ def gemm_desc(A, B, C_, *, trans_a=False, trans_b=False, bias=None, rowbias=None
     if accumulate:
         assert C_.dtype == torch.float32
     d.accumulate, d.split_k, d.force_simt = int(accumulate), split_k, int(force_simt)
+    if mul_aux is not None:
+        _chk2d(mul_aux)
+        assert mul_aux.shape == C_.shape and mul_aux.stride(0) == C_.stride(0)
+        d.mul_aux, d.mul_aux_dtype, d.mul_aux_act = mul_aux.data_ptr(), L.dt(mul_aux), mul_aux_act
     return d
 
 

@@ -94,3 +94,32 @@ def test_simt_fp32(ta, tb):
 
 def test_tc_matches_simt_on_bf16_inputs():
     _run(300, 384, 200, torch.bfloat16, force_simt=True, bias=True)
+
+
+def test_tc_fused_activation_backward():
+    """dgrad with the fused act'(pre) multiplier (QuickGELU / erf-GELU backward folded into the epilogue)."""
+    from segclip_b200 import ops
+    torch.manual_seed(0)
+    for act in (1, 2):
+        M, N, K = 392, 3072, 768
+        dy = torch.randn(M, K, device="cuda").bfloat16()
+        W = (torch.randn(K, N, device="cuda") * 0.05).bfloat16()
+        pre = torch.randn(M, N, device="cuda").bfloat16()
+        out = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
+        ops.gemm(dy, W, out, trans_b=True, mul_aux=pre, mul_aux_act=act)
+        x = pre.float().requires_grad_(True)
+        y = x * torch.sigmoid(1.702 * x) if act == 1 else torch.nn.functional.gelu(x)
+        y.backward(dy.float() @ W.float())
+        err = float((out.float() - x.grad).abs().max() / x.grad.abs().max())
+        assert err < 1e-2, err
+
+
+def test_colsum_vectorised_and_scalar():
+    from segclip_b200 import ops
+    torch.manual_seed(0)
+    for rows, cols, dt in [(5000, 3072, torch.bfloat16), (777, 768, torch.float32), (100, 36, torch.float32)]:
+        x = torch.randn(rows, cols, device="cuda").to(dt)
+        out = torch.zeros(cols, device="cuda")
+        ops.colsum_op(x, out)()
+        ref = x.float().sum(0)
+        assert float((out - ref).abs().max()) < 1e-3 * (1 + float(ref.abs().max()))
