@@ -354,9 +354,10 @@ def encode_image(image, p, cfg, u1, kv_layout, forced_idx=None):
     c = sx
     for i in range(12 - cfg["first_stage_layer"]):
         c = self_attn_block(c, p, f"{t}layers2.{i}.", heads)
-    cls = c.max(dim=1, keepdim=True)[0]
+    cls, pool_arg = c.max(dim=1, keepdim=True)
     hid = ln(torch.cat([cls, c], dim=1), p, v + "ln_post") @ p[v + "proj"]
-    return hid[:, 0], dict(hard_attn=hard, soft_attn=soft, assign=idx, patches=x, centers=c, hidden=hid)
+    return hid[:, 0], dict(hard_attn=hard, soft_attn=soft, assign=idx, patches=x, centers=c, hidden=hid,
+                           pool_arg=pool_arg[:, 0])
 
 
 def encode_image_mae(image, p, cfg, u2, u3, kv_layout, forced_idx=None):
@@ -462,7 +463,7 @@ def rank_forward(p, batch, noise, cfg, kv_layout="torch18_flat", forced=None):
     v, aux = encode_image(image, p, cfg, noise["u1"], kv_layout, forced.get("main"))
     extra = torch.zeros(())
     info = dict(assign_main=aux["assign"], hard_attn=aux["hard_attn"], soft_attn=aux["soft_attn"],
-                t_raw=t, v_raw=v)
+                t_raw=t, v_raw=v, pool_arg=aux["pool_arg"])
     if cfg["use_kl"]:
         info["kl"] = superpixel_kl(aux["hard_attn"], batch["image_seg"][:, 0])
         extra = extra + info["kl"]

@@ -1,6 +1,8 @@
 // HBM-bound glue kernels of the SegCLIP hot path: activation backward, bias gradients, parameter
 // shadow casts, patch extraction, embedding, row gather/scatter, MAE masking, pooling.
 // All are one-pass, coalesced along the feature dimension, fp32 math.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 extern void sc_count_launch(int n);
@@ -262,7 +264,8 @@ int sc_convert(const void* src, int src_dtype, void* dst, int dst_dtype, int64_t
 int sc_colsum(const void* x, int dtype, int64_t ld, int64_t rows, int cols, float* out, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
   SC_CHECK_ARG(x && out && rows > 0 && cols > 0, "sc_colsum: bad args");
-  if (cols % 8 == 0 && ld % 8 == 0 && ((uintptr_t)x & 15) == 0) {
+  static const bool force_scalar = getenv("SC_COLSUM_SCALAR") != nullptr;
+  if (!force_scalar && cols % 8 == 0 && ld % 8 == 0 && ((uintptr_t)x & 15) == 0) {
     const int gx = ceil_div(cols, 256);
     int gy = (int)((4L * sc_num_sms() + gx - 1) / gx);
     if (gy > ceil_div(rows, 32)) gy = ceil_div(rows, 32);

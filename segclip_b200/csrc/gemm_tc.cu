@@ -40,9 +40,9 @@ SC_DEVINL void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 SC_DEVINL void mbar_wait(uint64_t* bar, uint32_t parity) {
-  uint32_t addr = smem_u32(bar);
+  const uint32_t addr = smem_u32(bar);
   uint32_t done = 0;
-  long long t0 = clock64();
+  uint32_t spins = 0;
   while (true) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
@@ -52,7 +52,7 @@ SC_DEVINL void mbar_wait(uint64_t* bar, uint32_t parity) {
         : "r"(addr), "r"(parity)
         : "memory");
     if (done) break;
-    if (clock64() - t0 > 4000000000LL) {  // ~2 s: a protocol bug, fail loudly instead of hanging
+    if (++spins > (1u << 28)) {  // a protocol bug: fail loudly instead of hanging the GPU
       printf("segclip_b200 gemm_tc: mbarrier timeout (block %d thread %d)\n", blockIdx.x, threadIdx.x);
       __trap();
     }
@@ -93,6 +93,74 @@ SC_DEVINL void tmem_ld32(uint32_t taddr, float* v) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+// ---- compile-time specialised epilogues for the hot-path GEMMs (everything else: EF_GENERIC runtime path) ----
+enum : int {
+  EF_BIAS = 1,          // + bias[n]
+  EF_QGELU = 2,         // QuickGELU
+  EF_C2 = 4,            // also store the pre-activation (bf16)
+  EF_RESID = 8,         // + residual (fp32)
+  EF_OUT_F32 = 16,      // fp32 output (default bf16)
+  EF_MULAUX_QGELU = 32, // * QuickGELU'(aux) (fused activation backward, aux bf16)
+  EF_ATOMIC = 64,       // split-K: atomic accumulate into fp32 C
+  EF_GENERIC = 1 << 20
+};
+
+SC_DEVINL float tanh_fast(float x) {
+  float y;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+// x*sigmoid(1.702x) with one MUFU: sigmoid(y) = 0.5 + 0.5 tanh(y/2)
+SC_DEVINL float qgelu_fast(float x) { return x * fmaf(0.5f, tanh_fast(0.851f * x), 0.5f); }
+SC_DEVINL float qgelu_grad_fast(float x) {
+  const float s = fmaf(0.5f, tanh_fast(0.851f * x), 0.5f);
+  return s * fmaf(1.702f * x, 1.0f - s, 1.0f);
+}
+SC_DEVINL void sts128(uint32_t addr, float a, float b, float c, float d) {
+  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+SC_DEVINL float4 lds128(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
+  return v;
+}
+SC_DEVINL uint2 pack4_bf16(const float4& v) {
+  __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y), b = __floats2bfloat162_rn(v.z, v.w);
+  uint2 u;
+  u.x = *(uint32_t*)&a;
+  u.y = *(uint32_t*)&b;
+  return u;
+}
+
+template <int F>
+SC_DEVINL void epi4_fast(const EpiParams& p, int m, int n, float4 v, const float4& b4) {
+  if constexpr (F == EF_GENERIC) {
+    epi_store4(p, m, n, v);
+  } else {
+    const long off = (long)m * p.ldc + n;
+    if constexpr ((F & EF_BIAS) != 0) { v.x += b4.x; v.y += b4.y; v.z += b4.z; v.w += b4.w; }
+    if constexpr ((F & EF_C2) != 0) *(uint2*)((bf16*)p.C2 + off) = pack4_bf16(v);
+    if constexpr ((F & EF_QGELU) != 0) { v.x = qgelu_fast(v.x); v.y = qgelu_fast(v.y); v.z = qgelu_fast(v.z); v.w = qgelu_fast(v.w); }
+    if constexpr ((F & EF_MULAUX_QGELU) != 0) {
+      const uint2 u = *(const uint2*)((const bf16*)p.mul_aux + off);
+      const float2 a = __bfloat1622float2(*(const __nv_bfloat162*)&u.x), b = __bfloat1622float2(*(const __nv_bfloat162*)&u.y);
+      v.x *= qgelu_grad_fast(a.x); v.y *= qgelu_grad_fast(a.y); v.z *= qgelu_grad_fast(b.x); v.w *= qgelu_grad_fast(b.y);
+    }
+    if constexpr ((F & EF_RESID) != 0) {
+      const float4 r = *(const float4*)(p.residual + (long)m * p.ldr + n);
+      v.x += r.x; v.y += r.y; v.z += r.z; v.w += r.w;
+    }
+    if constexpr ((F & EF_ATOMIC) != 0) {
+      float* c = (float*)p.C + off;
+      atomicAdd(c, v.x); atomicAdd(c + 1, v.y); atomicAdd(c + 2, v.z); atomicAdd(c + 3, v.w);
+    } else if constexpr ((F & EF_OUT_F32) != 0) {
+      *(float4*)((float*)p.C + off) = v;
+    } else {
+      *(uint2*)((bf16*)p.C + off) = pack4_bf16(v);
+    }
+  }
+}
+
 // Shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout), SWIZZLE_128B.
 //   K-major : rows of 128 B, 8-row swizzle atoms 1024 B apart (SBO); LBO unused (1).
 //   MN-major: 64-element (128 B) MN chunks; k rows 128 B apart, 8-k-row atoms SBO=1024 B apart,
@@ -118,13 +186,13 @@ struct TileCfg {
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/ + NUM_EPI_WARPS * 4096;
 };
 
-template <int BN, bool A_MN, bool B_MN>
+template <int BN, bool A_MN, bool B_MN, int EF>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int tiles_m,
                int tiles_n, int splits, int kb_total, int kb_per_split, EpiParams ep) {
   using Cfg = TileCfg<BN>;
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  extern __shared__ __align__(1024) uint8_t smem[];
+  if ((smem_u32(smem) & 1023u) != 0u) __trap();   // 128B-swizzle atoms need a 1024-byte aligned base
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + Cfg::STAGES * Cfg::A_BYTES;
   uint64_t* bars = (uint64_t*)(smem + Cfg::STAGES * Cfg::STAGE_BYTES);
@@ -238,7 +306,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // =============================== epilogue ===============================
     const int quarter = warp & 3;       // TMEM lane quarter this warp may access
     const int half = warp >> 2;         // column half of the tile
-    uint8_t* stage = epi_stage + warp * 4096;
+    const uint32_t stage = smem_u32(epi_stage) + warp * 4096;
     int it = 0;
     for (int item = blockIdx.x; item < num_items; item += gridDim.x, ++it) {
       const int nt = item % tiles_n;
@@ -250,6 +318,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       tcgen05_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BN + half * (BN / 2);
       const int mrow0 = mt * BM + quarter * 32;
+      const int l7 = lane & 7, l3 = lane >> 3;
 #pragma unroll 1
       for (int c = 0; c < BN / 2 / 32; ++c) {
         float v[32];
@@ -259,15 +328,19 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         __syncwarp();
 #pragma unroll
         for (int j = 0; j < 8; ++j)
-          *(float4*)(stage + lane * 128 + ((j ^ (lane & 7)) << 4)) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+          sts128(stage + lane * 128 + ((j ^ l7) << 4), v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
         __syncwarp();
-        const int n = nbase + c * 32 + (lane & 7) * 4;
+        const int n = nbase + c * 32 + l7 * 4;
+        if (n < ep.N) {
+          float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+          if constexpr (EF != EF_GENERIC && (EF & EF_BIAS) != 0) b4 = __ldg((const float4*)(ep.bias + n));
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int r = 4 * i + (lane >> 3);
-          const float4 x = *(const float4*)(stage + r * 128 + (((lane & 7) ^ (r & 7)) << 4));
-          const int m = mrow0 + r;
-          if (m < ep.M && n < ep.N) epi_store4(ep, m, n, x);
+          for (int i = 0; i < 8; ++i) {
+            const int r = 4 * i + l3;
+            const float4 x = lds128(stage + r * 128 + ((l7 ^ (r & 7)) << 4));
+            const int m = mrow0 + r;
+            if (m < ep.M) epi4_fast<EF>(ep, m, n, x, b4);
+          }
         }
       }
       tcgen05_fence_before();
@@ -361,10 +434,10 @@ int get_tensor_map(const void* ptr, uint64_t dim0, uint64_t dim1, uint64_t strid
   return SC_OK;
 }
 
-template <int BN, bool A_MN, bool B_MN>
+template <int BN, bool A_MN, bool B_MN, int EF>
 int launch(const sc_gemm_desc* d, const CUtensorMap& ta, const CUtensorMap& tb, int splits, cudaStream_t st) {
   using Cfg = TileCfg<BN>;
-  auto kern = gemm_tc_kernel<BN, A_MN, B_MN>;
+  auto kern = gemm_tc_kernel<BN, A_MN, B_MN, EF>;
   static bool configured = false;  // per template instantiation
   if (!configured) {
     SC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
@@ -428,13 +501,47 @@ int sc_gemm_tc(const sc_gemm_desc* d, cudaStream_t st) {
   else rc = get_tensor_map(d->B, d->N, d->K, d->ldb, 64, BK, &tb);
   if (rc) return rc;
 
+  // epilogue specialisation
+  int ef = EF_GENERIC;
+  const bool simple = d->alpha == 1.0f && !d->rowbias && (!d->accumulate || splits > 1);
+  if (simple) {
+    const bool bias = d->bias != nullptr, resid = d->residual != nullptr, c2 = d->C2 != nullptr, aux = d->mul_aux != nullptr;
+    const bool out_bf16 = d->c_dtype == SC_BF16;
+    if (splits > 1) {
+      if (!bias && !resid && !c2 && !aux && d->act == SC_ACT_NONE) ef = EF_ATOMIC | EF_OUT_F32;
+    } else if (!aux && !c2 && !resid && d->act == SC_ACT_NONE && out_bf16) {
+      ef = bias ? EF_BIAS : 0;
+    } else if (bias && c2 && d->c2_dtype == SC_BF16 && out_bf16 && d->act == SC_ACT_QUICKGELU && !resid && !aux) {
+      ef = EF_BIAS | EF_QGELU | EF_C2;
+    } else if (bias && resid && !c2 && !aux && d->act == SC_ACT_NONE && !out_bf16) {
+      ef = EF_BIAS | EF_RESID | EF_OUT_F32;
+    } else if (aux && d->mul_aux_dtype == SC_BF16 && d->mul_aux_act == SC_ACT_QUICKGELU && !bias && !resid && !c2 &&
+               d->act == SC_ACT_NONE && out_bf16) {
+      ef = EF_MULAUX_QGELU;
+    }
+  }
   sc_count_launch(1);
-#define SC_DISPATCH(BN_)                                                            \
-  if (!a_mn && !b_mn) return launch<BN_, false, false>(d, ta, tb, splits, st);      \
-  if (!a_mn && b_mn) return launch<BN_, false, true>(d, ta, tb, splits, st);        \
-  if (a_mn && b_mn) return launch<BN_, true, true>(d, ta, tb, splits, st);          \
-  return launch<BN_, true, false>(d, ta, tb, splits, st);
+#define SC_L(BN_, A_, B_, EF_) return launch<BN_, A_, B_, EF_>(d, ta, tb, splits, st);
+#define SC_DISPATCH(BN_)                                                                     \
+  if (!a_mn && !b_mn) {                                                                      \
+    if (ef == EF_BIAS) SC_L(BN_, false, false, EF_BIAS)                                      \
+    if (ef == 0) SC_L(BN_, false, false, 0)                                                  \
+    if (ef == (EF_BIAS | EF_QGELU | EF_C2)) SC_L(BN_, false, false, EF_BIAS | EF_QGELU | EF_C2) \
+    if (ef == (EF_BIAS | EF_RESID | EF_OUT_F32)) SC_L(BN_, false, false, EF_BIAS | EF_RESID | EF_OUT_F32) \
+    SC_L(BN_, false, false, EF_GENERIC)                                                      \
+  }                                                                                          \
+  if (!a_mn && b_mn) {                                                                       \
+    if (ef == 0) SC_L(BN_, false, true, 0)                                                   \
+    if (ef == EF_MULAUX_QGELU) SC_L(BN_, false, true, EF_MULAUX_QGELU)                       \
+    SC_L(BN_, false, true, EF_GENERIC)                                                       \
+  }                                                                                          \
+  if (a_mn && b_mn) {                                                                        \
+    if (ef == (EF_ATOMIC | EF_OUT_F32)) SC_L(BN_, true, true, EF_ATOMIC | EF_OUT_F32)        \
+    SC_L(BN_, true, true, EF_GENERIC)                                                        \
+  }                                                                                          \
+  SC_L(BN_, true, false, EF_GENERIC)
   if (BN == 256) { SC_DISPATCH(256) }
   SC_DISPATCH(128)
 #undef SC_DISPATCH
+#undef SC_L
 }

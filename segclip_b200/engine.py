@@ -16,6 +16,8 @@ residual stream and its gradient are fp32, GEMM operands are in the compute dtyp
 mode or bf16).  Gradients that are shared by several consumers live in zero-initialised fp32 buffers
 and are accumulated.
 """
+import os
+
 import torch
 
 from . import _lib as L
@@ -248,7 +250,11 @@ class Engine:
             pl.f(ops.gemm_op(h2, self.W(pre + nm["w1"]), hact, bias=self.P(pre + nm["b1"]), act=act, C2=hpre))
             pl.f(ops.gemm_op(hact, self.W(pre + nm["w2"]), x_out, bias=self.P(pre + nm["b2"]), residual=x_mid))
             d_a, d_ln = sbuf("d_a", (M, Dh), T), sbuf("d_ln", (M, D), T)
-            grp = linear_bwd(dxT, hact, pre + nm["w2"], pre + nm["b2"], dx=d_a, mul_aux=hpre, mul_act=act)  # fused act'()
+            if os.environ.get("SC_NO_FUSE_ACT"):
+                grp = linear_bwd(dxT, hact, pre + nm["w2"], pre + nm["b2"], dx=d_a)
+                grp.append(ops.act_bwd_op(d_a, hpre, d_a, act))
+            else:
+                grp = linear_bwd(dxT, hact, pre + nm["w2"], pre + nm["b2"], dx=d_a, mul_aux=hpre, mul_act=act)  # fused act'()
             grp += linear_bwd(d_a, h2, pre + nm["w1"], pre + nm["b1"], dx=d_ln)
             grp.append(ln_bwd(d_ln, x_mid, st2, pre + nm["ln2"], dx, True, dxT))
             return grp
@@ -307,7 +313,7 @@ class Engine:
             dkvp = sbuf("dkvp", (Bn * S, 2 * D), T)
             d_qn, d_kvn = sbuf("d_ln", (Mq, D), T), sbuf("d_kvn", (Bn * S, D), T)
             grp = linear_bwd(dqT, o, pre + "attn.out_proj.weight", pre + "attn.out_proj.bias", dx=d_o)
-            grp.append(ops.attention_bwd_op(ad, d_o, dqp, dkvp, dkvp[:, D:]))
+            grp.append(ops.attention_bwd_op(ad, d_o, dqp, dkvp, dkvp[:, D:], sbuf("att_delta_x", (Bn, H, G), f32)))
             grp += linear_bwd(dqp, qn, pre + "attn.in_proj_weight", pre + "attn.in_proj_bias", dx=d_qn,
                               wslice=slice(0, D), bslice=slice(0, D))
             grp += linear_bwd(dkvp, kvn, pre + "attn.in_proj_weight", pre + "attn.in_proj_bias", dx=d_kvn,
@@ -445,6 +451,7 @@ class Engine:
             c = block(c, dc, dcT, f"{t_}layers2.{i}.", CLIP_BLOCK, f"v2_{i}", B, G, self.Hv)
         pooled, parg = buf("v.pooled", (B, D)), buf("v.parg", (B, D), i32)
         pl.f(ops.pool_max_op(c, pooled, parg, B, G, D))
+        pl.f("force_pool")      # test hook: teacher-forced arg-max routing of the max pooling
         hpv = buf("v.hp", (B, D), T)
         st_post = ln_fwd(pooled, "clip.visual.ln_post", hpv, "v.ln_post")
         v_raw = buf("v.raw", (B, self.E))
@@ -582,7 +589,11 @@ class Engine:
             op(st)
         for op in pl.fwd:
             if isinstance(op, str):
-                self._collective(op, pl)
+                if op == "force_pool":
+                    if use_forced and forced.get("pool") is not None:
+                        b["v.parg"].copy_(forced["pool"].to(torch.int32))
+                else:
+                    self._collective(op, pl)
             elif isinstance(op, tuple):
                 op[1 if use_forced else 0](st)
             else:
@@ -605,7 +616,8 @@ class Engine:
 
         def run(op):
             if isinstance(op, str):
-                self._collective(op, pl)
+                if op != "force_pool":
+                    self._collective(op, pl)
                 return
             if isinstance(op, tuple):
                 op = op[0]

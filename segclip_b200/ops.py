@@ -3,6 +3,7 @@
 Every function returns an ``Op`` -- (C function, argument tuple, tensors kept alive) -- that the
 engine replays each step with only the CUDA stream appended.  No arithmetic happens in Python."""
 import ctypes as C
+import os
 
 import torch
 
@@ -138,7 +139,7 @@ def attn_desc(q, k, v, o, lse, B, H, Lq, Lk, hd, q_str, k_str, v_str, o_str, cau
     a.v, (a.v_bs, a.v_rs) = v.data_ptr(), v_str
     a.o, (a.o_bs, a.o_rs) = o.data_ptr(), o_str
     a.lse = lse.data_ptr()
-    a.force_generic = int(force_generic)
+    a.force_generic = int(force_generic or bool(os.environ.get("SC_ATT_GENERIC")))
     return a
 
 

@@ -47,7 +47,7 @@ def _run(B, H, L, hd, dtype, causal=False, force_generic=False, seed=0):
 
 
 @pytest.mark.parametrize("B,H,L,hd,causal", [(3, 12, 196, 64, False), (2, 8, 77, 64, True), (2, 8, 197, 48, False),
-                                             (2, 12, 48, 64, False), (1, 2, 16, 32, False), (2, 4, 130, 64, True),
+                                             (2, 12, 48, 64, False), (1, 2, 16, 32, False), (3, 2, 16, 64, False), (3, 1, 16, 64, True), (2, 4, 130, 64, True),
                                              (1, 2, 577, 64, False)])
 def test_tensor_core_attention(B, H, L, hd, causal):
     _run(B, H, L, hd, torch.bfloat16, causal)
@@ -62,21 +62,35 @@ def test_generic_bf16_matches_too():
     _run(2, 12, 196, 64, torch.bfloat16, False, force_generic=True)
 
 
-def test_cross_attention_flat_kv_layout():
-    """K/V addressed with the torch-1.8 flat re-interpretation: slot b' key s = flat row s*B+b'."""
+@pytest.mark.parametrize("dtype,S", [(torch.float32, 24), (torch.bfloat16, 24), (torch.bfloat16, 204)])
+def test_cross_attention_flat_kv_layout(dtype, S):
+    """K/V addressed with the torch-1.8 flat re-interpretation: slot b' key s = flat row s*B+b'.
+    fp32 runs the generic kernel, bf16 the tensor-core kernels (8 query rows padded to one 16-row MMA tile)."""
     from segclip_b200 import ops
     torch.manual_seed(0)
-    B, H, hd, G, S = 3, 2, 64, 8, 24
+    B, H, hd, G = 3, 2, 64, 8
     D = H * hd
-    q = torch.randn(B * G, D, device="cuda")
-    kv = torch.randn(B * S, 2 * D, device="cuda")
-    o = torch.empty(B * G, D, device="cuda")
+    q = torch.randn(B * G, D, device="cuda").to(dtype)
+    kv = torch.randn(B * S, 2 * D, device="cuda").to(dtype)
+    do = torch.randn(B * G, D, device="cuda").to(dtype)
+    o = torch.empty(B * G, D, device="cuda", dtype=dtype)
     lse = torch.empty(B, H, G, device="cuda")
-    a = ops.attn_desc(q, kv, kv[:, D:], o, lse, B, H, G, S, hd, (G * D, D), (2 * D, B * 2 * D), (2 * D, B * 2 * D), (G * D, D))
+    kstr = (2 * D, B * 2 * D)
+    a = ops.attn_desc(q, kv, kv[:, D:], o, lse, B, H, G, S, hd, (G * D, D), kstr, kstr, (G * D, D))
     ops.attention_op(a)()
+    dq, dkv = torch.full_like(q, float("nan")), torch.full_like(kv, float("nan"))
+    ops.attention_bwd_op(a, do, dq, dkv, dkv[:, D:], torch.empty(B, H, G, device="cuda"))()
     torch.cuda.synchronize()
-    kf = kv[:, :D].reshape(S, B, D).transpose(0, 1)       # [B, S, D] as torch 1.8 saw it
-    vf = kv[:, D:].reshape(S, B, D).transpose(0, 1)
-    s = torch.einsum("bihd,bjhd->bhij", q.view(B, G, H, hd), kf.reshape(B, S, H, hd)) * hd ** -0.5
+    qf = q.float().requires_grad_(True)
+    kvf = kv.float().requires_grad_(True)
+    kf = kvf[:, :D].reshape(S, B, D).transpose(0, 1)       # [B, S, D] as torch 1.8 saw it
+    vf = kvf[:, D:].reshape(S, B, D).transpose(0, 1)
+    s = torch.einsum("bihd,bjhd->bhij", qf.view(B, G, H, hd), kf.reshape(B, S, H, hd)) * hd ** -0.5
     ref = torch.einsum("bhij,bjhd->bihd", torch.softmax(s, -1), vf.reshape(B, S, H, hd)).reshape(B * G, D)
-    assert float((o - ref).abs().max()) < 1e-4
+    ref.backward(do.float())
+    tol = 1e-4 if dtype == torch.float32 else 2e-2
+    def rel(x, y):
+        return float((x.float() - y).abs().max() / (y.abs().max() + 1e-9))
+    assert rel(o, ref.detach()) < tol
+    assert rel(dq, qf.grad) < tol, rel(dq, qf.grad)
+    assert rel(dkv, kvf.grad) < tol, rel(dkv, kvf.grad)

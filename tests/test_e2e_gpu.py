@@ -36,22 +36,25 @@ def test_fp32_loss_and_grads_match_oracle_and_golden(case):
 
 @pytest.mark.parametrize("case", ["toy_heads_flat", "vitb16_contrastive_b2", "vitb16_heads_b2"])
 def test_bf16_teacher_forced(case):
+    """bf16 compute vs the fp32 oracle with the two discrete decisions of the forward pass teacher-forced to the
+    oracle's (patch->centre arg-max; per-channel arg-max of the centre max-pooling, module_seg_vit.py:441):
+    a flipped arg-max reroutes a gradient, which is a property of the discontinuity, not an arithmetic error."""
     r = _run(case, "bf16", forced=True)
     assert r["loss_rel"] <= 1e-2, r["loss_rel"]
-    # Gradients: bf16 operand rounding through 12+ layers and a B=2 InfoNCE (a difference of two nearly equal
-    # softmax terms) gives a direction error of ~0.1 rad on every tensor (SURVEY F8 measured 0.09 for CPU bf16
-    # autocast against the same fp32 oracle); the fp32 mode of the very same kernels is exact to 1e-5.
     assert r["assign_flip_rate"] == 0.0
-    assert r["min_grad_cos"] >= 0.98, r["worst"][:5]
+    # measured: rel-L2 0.05-0.07, cosine >= 0.997 on every tensor (bf16 operand rounding through 12+ layers and a
+    # B=2 InfoNCE); the fp32 mode of the very same code path is exact to 1e-5.
+    assert r["min_grad_cos"] >= 0.99, r["worst"][:5]
     rels = sorted(v[0] for v in r["errs"].values())
-    assert rels[len(rels) // 2] <= 0.12, rels[len(rels) // 2]
-    assert rels[-1] <= 0.2, r["worst"][:5]
+    assert rels[len(rels) // 2] <= 0.08, rels[len(rels) // 2]
+    assert rels[-1] <= 0.15, r["worst"][:5]
 
 
-def test_bf16_unforced_loss_and_flip_rate():
-    r = _run("vitb16_contrastive_b2", "bf16", forced=False)
+def test_bf16_unforced_loss_and_flip_rates():
+    r = _run("vitb16_heads_b2", "bf16", forced=False)
     assert r["loss_rel"] <= 1e-2, r["loss_rel"]
     assert r["assign_flip_rate"] <= 0.02, r["assign_flip_rate"]
+    assert r["pool_flip_rate"] <= 0.05, r["pool_flip_rate"]
 
 
 def test_grad_output_scaling_and_repeatability():

@@ -39,7 +39,7 @@ def run_case(case, precision, forced=False, verbose=True):
     model = build_model(cfg, params, precision, kv)
     model.inject_noise({k: v.cuda() for k, v in noise.items()})
     if forced:
-        f = {"main": info["assign_main"].cuda()}
+        f = {"main": info["assign_main"].cuda(), "pool": info["pool_arg"].cuda()}
         if cfg["use_mae"]:
             f["mae"] = info["assign_mae"].cuda()
         model.force_assignment(f)
@@ -52,6 +52,7 @@ def run_case(case, precision, forced=False, verbose=True):
                golden_loss=g["loss"], loss_rel=abs(float(loss) - float(ref_loss)) / abs(float(ref_loss)))
     idx = bufs["v.sem.idx"].cpu().long()
     out["assign_flip_rate"] = float((idx != info["assign_main"]).float().mean())
+    out["pool_flip_rate"] = float((bufs["v.parg"].cpu().long() != info["pool_arg"]).float().mean())
     if cfg["use_mae"]:
         out["assign_flip_rate_mae"] = float((bufs["m.sem.idx"].cpu().long() != info["assign_mae"]).float().mean())
     errs = {}
