@@ -133,7 +133,7 @@ SC_DEVINL uint2 pack4_bf16(const float4& v) {
 }
 
 template <int F>
-SC_DEVINL void epi4_fast(const EpiParams& p, int m, int n, float4 v, const float4& b4) {
+SC_DEVINL void epi4_fast(const EpiParams& p, int m, int n, float4 v, const float4& b4, const float4& pre) {
   if constexpr (F == EF_GENERIC) {
     epi_store4(p, m, n, v);
   } else {
@@ -142,13 +142,12 @@ SC_DEVINL void epi4_fast(const EpiParams& p, int m, int n, float4 v, const float
     if constexpr ((F & EF_C2) != 0) *(uint2*)((bf16*)p.C2 + off) = pack4_bf16(v);
     if constexpr ((F & EF_QGELU) != 0) { v.x = qgelu_fast(v.x); v.y = qgelu_fast(v.y); v.z = qgelu_fast(v.z); v.w = qgelu_fast(v.w); }
     if constexpr ((F & EF_MULAUX_QGELU) != 0) {
-      const uint2 u = *(const uint2*)((const bf16*)p.mul_aux + off);
-      const float2 a = __bfloat1622float2(*(const __nv_bfloat162*)&u.x), b = __bfloat1622float2(*(const __nv_bfloat162*)&u.y);
+      const uint32_t ux = __float_as_uint(pre.x), uy = __float_as_uint(pre.y);   // prefetched bf16x4
+      const float2 a = __bfloat1622float2(*(const __nv_bfloat162*)&ux), b = __bfloat1622float2(*(const __nv_bfloat162*)&uy);
       v.x *= qgelu_grad_fast(a.x); v.y *= qgelu_grad_fast(a.y); v.z *= qgelu_grad_fast(b.x); v.w *= qgelu_grad_fast(b.y);
     }
     if constexpr ((F & EF_RESID) != 0) {
-      const float4 r = *(const float4*)(p.residual + (long)m * p.ldr + n);
-      v.x += r.x; v.y += r.y; v.z += r.z; v.w += r.w;
+      v.x += pre.x; v.y += pre.y; v.z += pre.z; v.w += pre.w;    // prefetched residual
     }
     if constexpr ((F & EF_ATOMIC) != 0) {
       float* c = (float*)p.C + off;
@@ -322,6 +321,29 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll 1
       for (int c = 0; c < BN / 2 / 32; ++c) {
         float v[32];
+        // issue the global reads of this chunk (bias, residual / activation-gradient operand) first: their DRAM latency
+        // overlaps the TMEM load and the smem transpose instead of serialising per row
+        const int n = nbase + c * 32 + l7 * 4;
+        float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        float4 pre[8];
+        if (n < ep.N) {
+          if constexpr (EF != EF_GENERIC && (EF & EF_BIAS) != 0) b4 = __ldg((const float4*)(ep.bias + n));
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int m = mrow0 + 4 * i + l3;
+            pre[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if constexpr (EF != EF_GENERIC && (EF & EF_RESID) != 0) {
+              if (m < ep.M) pre[i] = *(const float4*)(ep.residual + (long)m * ep.ldr + n);
+            }
+            if constexpr (EF != EF_GENERIC && (EF & EF_MULAUX_QGELU) != 0) {
+              if (m < ep.M) {
+                const uint2 u = *(const uint2*)((const bf16*)ep.mul_aux + (long)m * ep.ldc + n);
+                pre[i].x = __uint_as_float(u.x);
+                pre[i].y = __uint_as_float(u.y);
+              }
+            }
+          }
+        }
         tmem_ld32(taddr + c * 32, v);
         // transpose through the warp's private smem patch (32 rows x 128 B, 16-byte chunks XOR-swizzled by row)
         // so that global loads/stores of the epilogue are full-line: 8 lanes cover 32 consecutive columns of a row.
@@ -330,16 +352,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         for (int j = 0; j < 8; ++j)
           sts128(stage + lane * 128 + ((j ^ l7) << 4), v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
         __syncwarp();
-        const int n = nbase + c * 32 + l7 * 4;
         if (n < ep.N) {
-          float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
-          if constexpr (EF != EF_GENERIC && (EF & EF_BIAS) != 0) b4 = __ldg((const float4*)(ep.bias + n));
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
             const int r = 4 * i + l3;
             const float4 x = lds128(stage + r * 128 + ((l7 ^ (r & 7)) << 4));
             const int m = mrow0 + r;
-            if (m < ep.M) epi4_fast<EF>(ep, m, n, x, b4);
+            if (m < ep.M) epi4_fast<EF>(ep, m, n, x, b4, pre[i]);
           }
         }
       }

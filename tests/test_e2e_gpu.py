@@ -80,10 +80,11 @@ def test_grad_output_scaling_and_repeatability():
     l1, g1 = step(1.0)
     l2, g2 = step(0.5)
     l3, g3 = step(1.0)
-    assert l1 == l2 == l3
+    assert abs(l1 - l2) <= 1e-6 * abs(l1) and abs(l1 - l3) <= 1e-6 * abs(l1)     # atomics reorder fp32 sums only
     for n in g1:
-        assert torch.allclose(g2[n] * 2, g1[n], rtol=1e-4, atol=1e-7), n
-        assert torch.allclose(g3[n], g1[n], rtol=1e-4, atol=1e-7), n      # atomics reorder fp32 sums only
+        tol = 1e-5 * float(g1[n].abs().max()) + 1e-9
+        assert float((g2[n] * 2 - g1[n]).abs().max()) <= tol, n
+        assert float((g3[n] - g1[n]).abs().max()) <= tol, n
 
 
 def test_eval_mode_returns_none_and_cpu_is_refused():
