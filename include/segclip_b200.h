@@ -339,6 +339,25 @@ int sc_mae_unshuffle_bwd(const float* dx, const int32_t* ids_restore, void* d_em
 int sc_mae_loss(const void* pred, int dtype, const float* image, const float* mask, int B, int L1, int keep, int grid,
                 int patch, float gscale, float* loss, void* dpred, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * NVLink peer-to-peer all-gather of the contrastive head (replaces diffdist.functional.all_gather +
+ * torch.distributed.barrier(), modules/util_module.py:180-190 and modules/modeling.py:352-354).
+ * Set-up (once): every rank sc_p2p_alloc()s a data buffer + signal pad, the 64-byte IPC handles are exchanged
+ * out of band (torch.distributed all_gather_object) and opened with sc_p2p_open().
+ * Hot path: sc_p2p_allgather copies this rank's segments (host arrays srcs/nbytes/offs, <= 4) into the same byte
+ * offsets of EVERY peer's buffer with plain stores
+ * over NVLink, raises per-peer epoch flags (st.release.sys) and waits for the peers' flags (ld.acquire.sys);
+ * sc_p2p_release tells the peers that this rank is done reading epoch `epoch` (so they may overwrite).
+ * epoch must increase by 1 per exchange on every rank.  scratch: device uint32[2], zeroed once.
+ */
+int sc_p2p_alloc(int64_t bytes, void** buf, void** pad, void* buf_handle_out, void* pad_handle_out);
+int sc_p2p_open(const void* handle, void** ptr);
+int sc_p2p_close(void* ptr);
+int sc_p2p_free(void* buf, void* pad);
+int sc_p2p_allgather(int nseg, const void* const* srcs, const int64_t* nbytes, const int64_t* offs, void* const* peer_bufs,
+                     void* const* peer_pads, int rank, int world, uint32_t epoch, void* scratch, void* stream);
+int sc_p2p_release(void* const* peer_pads, int rank, int world, uint32_t epoch, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

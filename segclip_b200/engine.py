@@ -469,7 +469,13 @@ class Engine:
         # =============================================================== contrastive head
         # (modules/modeling.py:204-209,338-357)
         N = B * self.world
-        t_all, v_all = buf("c.t_all", (N, self.E)), buf("c.v_all", (N, self.E))
+        if self.world > 1:
+            if self.gather is None:
+                raise L.SegclipB200Error("world_size > 1: attach an exchange (segclip_b200.p2p.EmbeddingExchange) first")
+            t_all, v_all, lse_ext = self.gather.buffers(B, self.E)
+            pl.bufs["c.t_all"], pl.bufs["c.v_all"] = t_all, v_all
+        else:
+            t_all, v_all = buf("c.t_all", (N, self.E)), buf("c.v_all", (N, self.E))
         lo = self.rank * B
         t_n, v_n = t_all[lo:lo + B], v_all[lo:lo + B]
         t_inv, v_inv = buf("c.t_inv", (B,)), buf("c.v_inv", (B,))
@@ -479,7 +485,11 @@ class Engine:
         raw_t2v, raw_v2t = buf("c.t2v", (B, N)), buf("c.v2t", (B, N))
         pl.f(ops.gemm_op(t_n, v_all, raw_t2v))
         pl.f(ops.gemm_op(v_n, t_all, raw_v2t))
-        lse_all = buf("c.lse_all", (2, N))            # [0] = t2v rows, [1] = v2t rows, global order
+        if self.world > 1:
+            lse_all = lse_ext
+            pl.bufs["c.lse_all"] = lse_all
+        else:
+            lse_all = buf("c.lse_all", (2, N))        # [0] = t2v rows, [1] = v2t rows, global order
         scale_p = self.P("clip.logit_scale")
         pl.f(ops.ce_lse_op(raw_t2v, lo, scale_p, lse_all[0, lo:lo + B], loss))
         pl.f(ops.ce_lse_op(raw_v2t, lo, scale_p, lse_all[1, lo:lo + B], loss))
@@ -490,6 +500,7 @@ class Engine:
                ops.ce_grad_op(raw_v2t, lo, scale_p, lse_all[1, lo:lo + B], lse_all[0], g_scale),
                ops.gemm_op(raw_t2v, v_all, d_tn, trans_b=True),
                ops.gemm_op(raw_v2t, t_all, d_vn, trans_b=True),
+               "release_exchange",          # last reader of the gathered embeddings / LSEs is done
                ops.l2norm_bwd_op(d_tn, t_n, t_inv, d_traw),
                ops.l2norm_bwd_op(d_vn, v_n, v_inv, d_vraw)]
         pl.b(grp)
@@ -604,7 +615,10 @@ class Engine:
         pl = self.plan(B)
         st = L.stream()
         for op in pl.bwd:
-            op(st)
+            if isinstance(op, str):
+                self._collective(op, pl)
+            else:
+                op(st)
         return self.gflat
 
     def profile_gemm(self, B):
@@ -644,9 +658,14 @@ class Engine:
 
     def _collective(self, what, pl):
         if self.world == 1:
-            if what == "gather_lse":
-                return
             return
         if self.gather is None:
             raise L.SegclipB200Error("world_size > 1 but no embedding exchange is attached to the engine")
-        self.gather(what, pl)
+        if what == "gather_embeddings":
+            self.gather.gather_embeddings()
+        elif what == "gather_lse":
+            self.gather.gather_lse()
+        elif what == "release_exchange":
+            self.gather.release()
+        else:
+            raise L.SegclipB200Error("unknown collective step %r" % what)

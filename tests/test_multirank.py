@@ -1,0 +1,109 @@
+"""Multi-rank path.
+
+CPU (gloo, world_size 2): the library-collective comparator exchange fills the gathered buffers in rank order.
+GPU (needs >= 2 devices, `gpurun --gpus 2`): two ranks of the real CUDA path -- once with the NVLink P2P write
+kernel and once with the NCCL comparator -- reproduce the 2-rank fixture of the unmodified reference (diffdist
+all-gather + DDP gradient mean, tests/golden/toy_heads_flat_w2.json)."""
+import argparse
+import os
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from tests.golden_util import compare_grads, load_case
+
+
+def _cpu_worker(rank, world, port, q):
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from segclip_b200.p2p import EmbeddingExchange
+    ex = EmbeddingExchange(dist.group.WORLD, "cpu")
+    B, E = 3, 8
+    t_all, v_all, lse_all = ex.buffers(B, E)
+    lo = rank * B
+    t_all[lo:lo + B] = rank + 1
+    v_all[lo:lo + B] = 10 * (rank + 1)
+    lse_all[0, lo:lo + B] = 100 + rank
+    lse_all[1, lo:lo + B] = 200 + rank
+    ex.gather_embeddings()
+    ex.gather_lse()
+    ex.release()
+    ok = all(float(t_all[r * B:(r + 1) * B].mean()) == r + 1 and float(v_all[r * B:(r + 1) * B].mean()) == 10 * (r + 1) and
+             float(lse_all[0, r * B]) == 100 + r and float(lse_all[1, r * B + B - 1]) == 200 + r for r in range(world))
+    q.put((rank, ok))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_collective_exchange_gloo_world2():
+    ctx = mp.get_context("spawn")
+    q = ctx.SimpleQueue()
+    procs = [ctx.Process(target=_cpu_worker, args=(r, 2, 29561, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = dict(q.get() for _ in range(2))
+    for p in procs:
+        p.join()
+    assert res == {0: True, 1: True}
+
+
+def _gpu_worker(rank, world, port, mode, q):
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    os.environ["SEGCLIP_EXCHANGE"] = mode
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    from oracle import ref_harness as rh
+    from oracle import segclip_oracle as so
+    from segclip_b200.engine import FROZEN_STEM
+    from segclip_b200.modeling import SegCLIP
+    from segclip_b200.p2p import EmbeddingExchange
+    g = load_case("toy_heads_flat_w2")
+    cfg = g["config"]
+    args = argparse.Namespace(local_rank=rank, rank=rank, world_size=world, first_stage_layer=cfg["first_stage_layer"],
+                              use_vision_mae_recon=True, use_seglabel=True, precision="fp32", kv_layout=g["kv_layout"])
+    model = SegCLIP(rh.fake_clip_state_dict(cfg), args)
+    model.load_state_dict(so.init_params(cfg, seed=g["param_seed"]), strict=False)
+    model = model.to(dev).train()
+    model.attach_exchange(EmbeddingExchange(dist.group.WORLD, dev))
+    batch, noise = so.make_batch(cfg, g["batch"], seed=g["batch_seed"], rank=rank)
+    model.inject_noise({k: v.to(dev) for k, v in noise.items()})
+    ids = batch["input_ids"]
+    losses = []
+    for _ in range(2):                      # two steps: exercises the epoch / release protocol
+        model.zero_grad(set_to_none=True)
+        loss = model(ids, torch.zeros_like(ids), batch["attention_mask"], batch["image"], image_seg=batch["image_seg"])
+        loss.backward()
+        losses.append(float(loss.detach()))
+    grads = {}
+    for n, p in model.named_parameters():
+        if p.grad is not None:
+            gr = p.grad.detach().clone()
+            dist.all_reduce(gr)
+            grads[n] = (gr / world).cpu()
+    bad = compare_grads(grads, g["grads"], tol=1e-3, skip=FROZEN_STEM) if rank == 0 else []
+    q.put((rank, losses, g["loss"][rank], bad[:5]))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("mode", ["p2p", "nccl"])
+def test_two_ranks_match_reference_fixture(mode):
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (gpurun --gpus 2)")
+    ctx = mp.get_context("spawn")
+    q = ctx.SimpleQueue()
+    port = 29571 if mode == "p2p" else 29573
+    procs = [ctx.Process(target=_gpu_worker, args=(r, 2, port, mode, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get() for _ in range(2)]
+    for p in procs:
+        p.join(120)
+    for rank, losses, want, bad in res:
+        for l in losses:
+            assert abs(l - want) <= 1e-3 * abs(want), (rank, losses, want)
+        assert not bad, bad
