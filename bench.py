@@ -164,7 +164,7 @@ def main():
     if world > 1:
         from segclip_b200.p2p import EmbeddingExchange
         model.attach_exchange(EmbeddingExchange(dist.group.WORLD, dev))
-        net = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local], find_unused_parameters=False,
+        net = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local], find_unused_parameters=True,
                                                         gradient_as_bucket_view=True)
     B = args.batch
     host = synthetic_batch(cfg, B, 0, rank, args.heads)

@@ -37,7 +37,7 @@ SC_DEVINL uint32_t ld_acquire_sys(const uint32_t* p) {
 SC_DEVINL void spin_until(const uint32_t* p, uint32_t epoch) {
   unsigned long long spins = 0;
   while ((int)(ld_acquire_sys(p) - epoch) < 0) {
-    if (++spins > (1ull << 31)) {
+    if (++spins > (1ull << 24)) {   // ~10 s: a peer died or the protocol is broken
       printf("segclip_b200 p2p: peer flag timeout (want epoch %u, have %u)\n", epoch, ld_acquire_sys(p));
       __trap();
     }

@@ -629,9 +629,7 @@ class Engine:
         recs = []
 
         def run(op):
-            if isinstance(op, str):
-                if op != "force_pool":
-                    self._collective(op, pl)
+            if isinstance(op, str):      # exchanges are skipped: this instrumented pass may run on one rank only
                 return
             if isinstance(op, tuple):
                 op = op[0]

@@ -203,8 +203,8 @@ class _NativeStep(torch.autograd.Function):
         scale = gout.detach().to(torch.float32).contiguous().view(1)
         ops.convert_op(gflat, out, scale)()          # grad * grad_output, read on the device
         grads = []
-        for name, p in owner._param_items:
-            if name in eng.grads and p.requires_grad and name not in owner._untouched:
+        for name, p in owner._active_items:
+            if p.requires_grad:
                 o = eng.goffs[name]
                 grads.append(out[o:o + p.numel()].view(p.shape))
             else:
@@ -299,6 +299,11 @@ class SegCLIP(nn.Module):
             self._untouched = set()
             if not self.cfg["use_mae"]:
                 self._untouched = {n for n in named if ".layers_mae2." in n or ".reconstruct_layer2." in n}
+            # parameters that take part in this configuration's graph; the others (MAE-only branches when the MAE
+            # head is off) stay outside autograd exactly like the reference's unused parameters (DDP is built with
+            # find_unused_parameters=True there, main_task_align.py:251-252)
+            self._active_items = [(n, p) for n, p in named.items()
+                                  if n in self._engine.grads and n not in self._untouched]
             if self._exchange is not None:
                 self._engine.gather = self._exchange
         return self._engine
@@ -346,7 +351,7 @@ class SegCLIP(nn.Module):
                 noise["u2"] = torch.rand(b, c.Lp + 1, device=dev)
                 noise["u3"] = torch.rand(b, G, c.Lm, device=dev)
         inputs = dict(ids=ids, image=img, seg=seg)
-        params = [p for _, p in self._param_items]
+        params = [p for _, p in self._active_items]
         return _NativeStep.apply(self, b, inputs, noise, self._forced, *params)
 
     # ---- introspection used by tests -----------------------------------------------------------
