@@ -13,7 +13,7 @@
 
 namespace {
 
-constexpr int AW = 8;              // warps per CTA
+constexpr int AW = 8;              // max warps per CTA (each warp loops over 16-row blocks)
 constexpr int AT = AW * 32;
 constexpr float LOG2E = 1.4426950408889634f;
 
@@ -47,16 +47,27 @@ SC_DEVINL float quad_sum(float v) {
 // smem tile: rows of 128 B (64 bf16; HD < 64 leaves the tail unused), 16-byte chunks XOR-swizzled by row&7
 SC_DEVINL uint32_t sw(int row, int chunk) { return (uint32_t)(row * 128 + ((chunk ^ (row & 7)) << 4)); }
 
-// Stage `rows` rows (zero beyond) of a [*, HD] slice with row stride rs into a swizzled tile of rows_pad rows.
+// Stage `rows` rows (zero beyond) of a [*, HD] slice with row stride rs into a swizzled tile of rows_pad rows,
+// asynchronously (LDGSTS: no register round trip); complete with stage_wait().
 template <int HD>
 SC_DEVINL void stage_tile(uint8_t* dst, const bf16* src, long rs, int rows, int rows_pad) {
   constexpr int CH = HD / 8;
-  for (int idx = threadIdx.x; idx < rows_pad * CH; idx += AT) {
+  const uint32_t d0 = smem_addr(dst);
+  for (int idx = threadIdx.x; idx < rows_pad * CH; idx += blockDim.x) {
     const int r = idx / CH, c = idx - r * CH;
-    uint4 v = make_uint4(0u, 0u, 0u, 0u);
-    if (r < rows) v = *(const uint4*)(src + (long)r * rs + c * 8);
-    *(uint4*)(dst + sw(r, c)) = v;
+    const bf16* g = src + (long)(r < rows ? r : 0) * rs + c * 8;
+    const int nbytes = r < rows ? 16 : 0;      // src-size 0 -> 16 bytes of zeros
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d0 + sw(r, c)), "l"(g), "r"(nbytes) : "memory");
   }
+}
+SC_DEVINL void stage_wait() {
+  asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
+  __syncthreads();
+}
+SC_DEVINL float ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
 }
 
 // A fragments (16 rows x HD) of a row-major global matrix; rows >= nrows read as zero.
@@ -132,14 +143,14 @@ __global__ void __launch_bounds__(AT, 2) attn_fwd_mma_kernel(sc_attn_desc a, int
   const int Lq = a.Lq, Lk = a.Lk;
   stage_tile<HD>(sK, (const bf16*)a.k + (long)b * a.k_bs + h * HD, a.k_rs, Lk, lk_pad);
   stage_tile<HD>(sV, (const bf16*)a.v + (long)b * a.v_bs + h * HD, a.v_rs, Lk, lk_pad);
-  __syncthreads();
-  const int row0 = blockIdx.x * (AW * 16) + warp * 16;
-  if (row0 >= Lq) return;
-  const bf16* qb = (const bf16*)a.q + (long)b * a.q_bs + h * HD;
-  uint32_t qf[HD / 16][4];
-  load_a_frags<HD>(qf, qb, a.q_rs, row0, Lq, lane);
+  stage_wait();
   const uint32_t tK = smem_addr(sK), tV = smem_addr(sV);
   const float c = a.scale * LOG2E;
+  const bf16* qb = (const bf16*)a.q + (long)b * a.q_bs + h * HD;
+  const int nwarps = blockDim.x >> 5;
+  for (int row0 = warp * 16; row0 < Lq; row0 += nwarps * 16) {
+  uint32_t qf[HD / 16][4];
+  load_a_frags<HD>(qf, qb, a.q_rs, row0, Lq, lane);
   float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;
   float o[HD / 8][4];
 #pragma unroll
@@ -152,22 +163,27 @@ __global__ void __launch_bounds__(AT, 2) attn_fwd_mma_kernel(sc_attn_desc a, int
     for (int j = 0; j < 8; ++j) s[j][0] = s[j][1] = s[j][2] = s[j][3] = 0.f;
     mma_a_tileT<HD, 4>(s, qf, tK, kb, np, lane);
     float mx0 = -INFINITY, mx1 = -INFINITY;
+    const bool need_mask = (kb + 64 > kend) || (CAUSAL && kb + 64 > row0);     // warp-uniform
+    if (need_mask) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int col = kb + j * 8 + 2 * t + (e & 1);
+          const int row = row0 + g + ((e >> 1) << 3);
+          const bool ok = col < kend && (!CAUSAL || col <= row);
+          s[j][e] = ok ? s[j][e] : -INFINITY;
+        }
+    }
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-#pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const int col = kb + j * 8 + 2 * t + (e & 1);
-        const int row = row0 + g + ((e >> 1) << 3);
-        const bool ok = col < kend && (!CAUSAL || col <= row);
-        s[j][e] = ok ? s[j][e] : -INFINITY;
-      }
       mx0 = fmaxf(mx0, fmaxf(s[j][0], s[j][1]));
       mx1 = fmaxf(mx1, fmaxf(s[j][2], s[j][3]));
     }
     mx0 = quad_max(mx0);
     mx1 = quad_max(mx1);
     const float n0 = fmaxf(m0, mx0), n1 = fmaxf(m1, mx1);
-    const float al0 = exp2f((m0 - n0) * c), al1 = exp2f((m1 - n1) * c);
+    const float al0 = ex2((m0 - n0) * c), al1 = ex2((m1 - n1) * c);
     m0 = n0;
     m1 = n1;
     l0 *= al0;
@@ -179,10 +195,10 @@ __global__ void __launch_bounds__(AT, 2) attn_fwd_mma_kernel(sc_attn_desc a, int
     const float mc0 = m0 * c, mc1 = m1 * c;
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      s[j][0] = exp2f(s[j][0] * c - mc0);
-      s[j][1] = exp2f(s[j][1] * c - mc0);
-      s[j][2] = exp2f(s[j][2] * c - mc1);
-      s[j][3] = exp2f(s[j][3] * c - mc1);
+      s[j][0] = ex2(fmaf(s[j][0], c, -mc0));
+      s[j][1] = ex2(fmaf(s[j][1], c, -mc0));
+      s[j][2] = ex2(fmaf(s[j][2], c, -mc1));
+      s[j][3] = ex2(fmaf(s[j][3], c, -mc1));
       l0 += s[j][0] + s[j][1];
       l1 += s[j][2] + s[j][3];
     }
@@ -204,6 +220,7 @@ __global__ void __launch_bounds__(AT, 2) attn_fwd_mma_kernel(sc_attn_desc a, int
     if (row0 + g < Lq) lse[row0 + g] = m0 * a.scale + logf(l0);
     if (row0 + g + 8 < Lq) lse[row0 + g + 8] = m1 * a.scale + logf(l1);
   }
+  }   // row-block loop
 }
 
 // =================================================================================== backward: dQ (+ delta)
@@ -219,10 +236,10 @@ __global__ void __launch_bounds__(AT, 2) attn_bwd_dq_mma_kernel(sc_attn_bwd_desc
   const int Lq = a.Lq, Lk = a.Lk;
   stage_tile<HD>(sK, (const bf16*)a.k + (long)b * a.k_bs + h * HD, a.k_rs, Lk, lk_pad);
   stage_tile<HD>(sV, (const bf16*)a.v + (long)b * a.v_bs + h * HD, a.v_rs, Lk, lk_pad);
-  __syncthreads();
-  const int row0 = blockIdx.x * (AW * 16) + warp * 16;
-  if (row0 >= Lq) return;
+  stage_wait();
   const long qoff = (long)b * a.q_bs + h * HD, ooff = (long)b * a.o_bs + h * HD;
+  const int nwarps = blockDim.x >> 5;
+  for (int row0 = warp * 16; row0 < Lq; row0 += nwarps * 16) {
   uint32_t qf[HD / 16][4], dof[HD / 16][4];
   load_a_frags<HD>(qf, (const bf16*)a.q + qoff, a.q_rs, row0, Lq, lane);
   load_a_frags<HD>(dof, (const bf16*)gd.d_o + ooff, a.o_rs, row0, Lq, lane);
@@ -274,7 +291,7 @@ __global__ void __launch_bounds__(AT, 2) attn_bwd_dq_mma_kernel(sc_attn_bwd_desc
         const int col = kb + j * 8 + 2 * t + (e & 1);
         const int row = row0 + g + ((e >> 1) << 3);
         const bool ok = col < kend && (!CAUSAL || col <= row);
-        const float p = ok ? exp2f(s[j][e] * c - ((e >> 1) ? lse1 : lse0)) : 0.f;
+        const float p = ok ? ex2(fmaf(s[j][e], c, -((e >> 1) ? lse1 : lse0))) : 0.f;
         s[j][e] = p * (dp[j][e] - ((e >> 1) ? d1 : d0));     // dS
       }
 #pragma unroll
@@ -287,6 +304,7 @@ __global__ void __launch_bounds__(AT, 2) attn_bwd_dq_mma_kernel(sc_attn_bwd_desc
     }
   }
   store_rows<HD>((bf16*)gd.d_q + qoff, a.q_rs, row0, Lq, dq, a.scale, a.scale, lane);
+  }   // row-block loop
 }
 
 // =================================================================================== backward: dK, dV
@@ -305,14 +323,14 @@ __global__ void __launch_bounds__(AT, 1) attn_bwd_dkv_mma_kernel(sc_attn_bwd_des
   const int Lq = a.Lq, Lk = a.Lk;
   stage_tile<HD>(sQ, (const bf16*)a.q + (long)b * a.q_bs + h * HD, a.q_rs, Lq, lq_pad);
   stage_tile<HD>(sdO, (const bf16*)gd.d_o + (long)b * a.o_bs + h * HD, a.o_rs, Lq, lq_pad);
-  for (int i = threadIdx.x; i < lq_pad; i += AT) {
+  for (int i = threadIdx.x; i < lq_pad; i += blockDim.x) {
     const long o = ((long)b * a.H + h) * Lq + i;
     sLse[i] = i < Lq ? a.lse[o] * LOG2E : 0.f;
     sDelta[i] = i < Lq ? delta[o] : 0.f;
   }
-  __syncthreads();
-  const int key0 = blockIdx.x * (AW * 16) + warp * 16;
-  if (key0 >= Lk) return;
+  stage_wait();
+  const int nwarps = blockDim.x >> 5;
+  for (int key0 = warp * 16; key0 < Lk; key0 += nwarps * 16) {
   const long koff = (long)b * a.k_bs + h * HD, voff = (long)b * a.v_bs + h * HD;
   uint32_t kf[HD / 16][4], vf[HD / 16][4];
   load_a_frags<HD>(kf, (const bf16*)a.k + koff, a.k_rs, key0, Lk, lane);
@@ -343,7 +361,7 @@ __global__ void __launch_bounds__(AT, 1) attn_bwd_dkv_mma_kernel(sc_attn_bwd_des
         const int qi = q0 + j * 8 + 2 * t + (e & 1);
         const int key = key0 + g + ((e >> 1) << 3);
         const bool ok = qi < Lq && (!CAUSAL || key <= qi);
-        const float p = ok ? exp2f(st[j][e] * c - sLse[qi]) : 0.f;
+        const float p = ok ? ex2(fmaf(st[j][e], c, -sLse[qi])) : 0.f;
         pt[j][e] = p;
         st[j][e] = p * (dpt[j][e] - sDelta[qi]);       // dS^T
       }
@@ -354,6 +372,7 @@ __global__ void __launch_bounds__(AT, 1) attn_bwd_dkv_mma_kernel(sc_attn_bwd_des
   }
   store_rows<HD>((bf16*)gd.d_k + koff, a.k_rs, key0, Lk, dk, a.scale, a.scale, lane);
   store_rows<HD>((bf16*)gd.d_v + voff, a.v_rs, key0, Lk, dv, 1.f, 1.f, lane);
+  }   // key-block loop
 }
 
 template <typename K>
@@ -382,16 +401,24 @@ bool sc_attn_mma_supported(const sc_attn_desc* a) {
   else if (a->hd == 48) { if (a->causal) { CALL(48, true) } else { CALL(48, false) } } \
   else { if (a->causal) { CALL(32, true) } else { CALL(32, false) } }
 
+// threads per CTA: every warp loops over 16-row blocks; pick the warp count that balances the passes
+static int att_threads(int rows) {
+  const int nblocks = (rows + 15) / 16;
+  const int passes = (nblocks + AW - 1) / AW;
+  return ((nblocks + passes - 1) / passes) * 32;
+}
+
 int sc_attention_fwd_mma(const sc_attn_desc* a, cudaStream_t st) {
-  const int lk_pad = (a->Lk + 63) & ~63;
+  const int lk_pad = (a->Lk + 15) & ~15;
   const size_t smem = (size_t)2 * lk_pad * 128;
-  dim3 grid((a->Lq + AW * 16 - 1) / (AW * 16), a->H, a->B);
+  dim3 grid(1, a->H, a->B);
+  const int AT_ = att_threads(a->Lq);
   sc_count_launch(1);
 #define CALL(HD_, C_)                                                                  \
   {                                                                                    \
     int rc = set_smem_attr(attn_fwd_mma_kernel<HD_, C_>, smem);                        \
     if (rc) return rc;                                                                 \
-    attn_fwd_mma_kernel<HD_, C_><<<grid, AT, smem, st>>>(*a, lk_pad);                  \
+    attn_fwd_mma_kernel<HD_, C_><<<grid, AT_, smem, st>>>(*a, lk_pad);                  \
   }
   SC_ATT_DISPATCH(CALL)
 #undef CALL
@@ -402,11 +429,11 @@ int sc_attention_fwd_mma(const sc_attn_desc* a, cudaStream_t st) {
 // delta: fp32 scratch [B, H, Lq] provided by the caller through the lse-sized workspace below
 int sc_attention_bwd_mma(const sc_attn_bwd_desc* g, float* delta, cudaStream_t st) {
   const sc_attn_desc* a = &g->fwd;
-  const int lk_pad = (a->Lk + 31) & ~31, lq_pad = (a->Lq + 15) & ~15;
+  const int lk_pad = (a->Lk + 15) & ~15, lq_pad = (a->Lq + 15) & ~15;
   const size_t smem_q = (size_t)2 * lk_pad * 128;
   const size_t smem_kv = (size_t)2 * lq_pad * 128 + 2 * lq_pad * sizeof(float);
-  dim3 grid_q((a->Lq + AW * 16 - 1) / (AW * 16), a->H, a->B);
-  dim3 grid_kv((a->Lk + AW * 16 - 1) / (AW * 16), a->H, a->B);
+  dim3 grid_q(1, a->H, a->B), grid_kv(1, a->H, a->B);
+  const int tq = att_threads(a->Lq), tkv = att_threads(a->Lk);
   sc_count_launch(2);
 #define CALL(HD_, C_)                                                                          \
   {                                                                                            \
@@ -414,8 +441,8 @@ int sc_attention_bwd_mma(const sc_attn_bwd_desc* g, float* delta, cudaStream_t s
     if (rc) return rc;                                                                         \
     rc = set_smem_attr(attn_bwd_dkv_mma_kernel<HD_, C_>, smem_kv);                             \
     if (rc) return rc;                                                                         \
-    attn_bwd_dq_mma_kernel<HD_, C_><<<grid_q, AT, smem_q, st>>>(*g, delta, lk_pad);            \
-    attn_bwd_dkv_mma_kernel<HD_, C_><<<grid_kv, AT, smem_kv, st>>>(*g, delta, lq_pad);         \
+    attn_bwd_dq_mma_kernel<HD_, C_><<<grid_q, tq, smem_q, st>>>(*g, delta, lk_pad);            \
+    attn_bwd_dkv_mma_kernel<HD_, C_><<<grid_kv, tkv, smem_kv, st>>>(*g, delta, lq_pad);         \
   }
   SC_ATT_DISPATCH(CALL)
 #undef CALL
