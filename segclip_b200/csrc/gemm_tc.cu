@@ -11,169 +11,117 @@
 // atomics (wgrad: K = batch*tokens, output only a few dozen tiles).
 #include <cuda.h>
 
+#include <stdlib.h>
+
 #include <mutex>
 #include <unordered_map>
 
-#include "common.cuh"
-#include "epilogue.cuh"
+#include "gemm_tc_common.cuh"
 
-namespace {
-
-constexpr int BM = 128;
-constexpr int BK = 64;  // 64 bf16 = 128 B = one swizzle row
-constexpr int NUM_EPI_WARPS = 8;
-constexpr int NUM_THREADS = (NUM_EPI_WARPS + 2) * 32;
-
+// ---- host helpers shared with gemm_tc2.cu ----
 // ---------------------------------------------------------------------------------------------
-// PTX wrappers
+// host side: tensor-map cache + dispatch
 // ---------------------------------------------------------------------------------------------
-SC_DEVINL uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
-SC_DEVINL void mbar_init(uint64_t* bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)p;
+  });
+  return fn;
 }
-SC_DEVINL void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
-               : "memory");
-}
-SC_DEVINL void mbar_arrive(uint64_t* bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-SC_DEVINL void mbar_wait(uint64_t* bar, uint32_t parity) {
-  const uint32_t addr = smem_u32(bar);
-  uint32_t done = 0;
-  uint32_t spins = 0;
-  while (true) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(done)
-        : "r"(addr), "r"(parity)
-        : "memory");
-    if (done) break;
-    if (++spins > (1u << 28)) {  // a protocol bug: fail loudly instead of hanging the GPU
-      printf("segclip_b200 gemm_tc: mbarrier timeout (block %d thread %d)\n", blockIdx.x, threadIdx.x);
-      __trap();
-    }
+
+struct MapKey {
+  const void* ptr;
+  uint64_t d0, d1, stride;
+  uint32_t b0, b1;
+  bool operator==(const MapKey& o) const {
+    return ptr == o.ptr && d0 == o.d0 && d1 == o.d1 && stride == o.stride && b0 == o.b0 && b1 == o.b1;
   }
-}
-SC_DEVINL void tma_load_2d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-      ::"r"(smem_u32(dst)), "l"((uint64_t)map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
-      : "memory");
-}
-SC_DEVINL void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-SC_DEVINL void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-SC_DEVINL void tcgen05_commit(uint64_t* bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
-               : "memory");
-}
-SC_DEVINL void tcgen05_mma_f16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accum) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accum)
-      : "memory");
-}
-SC_DEVINL void tmem_ld32(uint32_t taddr, float* v) {
-  uint32_t* r = (uint32_t*)v;
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
-        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
-        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-      : "r"(taddr)
-      : "memory");
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-}
-
-// ---- compile-time specialised epilogues for the hot-path GEMMs (everything else: EF_GENERIC runtime path) ----
-enum : int {
-  EF_BIAS = 1,          // + bias[n]
-  EF_QGELU = 2,         // QuickGELU
-  EF_C2 = 4,            // also store the pre-activation (bf16)
-  EF_RESID = 8,         // + residual (fp32)
-  EF_OUT_F32 = 16,      // fp32 output (default bf16)
-  EF_MULAUX_QGELU = 32, // * QuickGELU'(aux) (fused activation backward, aux bf16)
-  EF_ATOMIC = 64,       // split-K: atomic accumulate into fp32 C
-  EF_GENERIC = 1 << 20
+};
+struct MapKeyHash {
+  size_t operator()(const MapKey& k) const {
+    size_t h = (size_t)k.ptr;
+    h = h * 1000003u ^ k.d0;
+    h = h * 1000003u ^ k.d1;
+    h = h * 1000003u ^ k.stride;
+    h = h * 1000003u ^ ((uint64_t)k.b0 << 32 | k.b1);
+    return h;
+  }
 };
 
-SC_DEVINL float tanh_fast(float x) {
-  float y;
-  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
-  return y;
-}
-// x*sigmoid(1.702x) with one MUFU: sigmoid(y) = 0.5 + 0.5 tanh(y/2)
-SC_DEVINL float qgelu_fast(float x) { return x * fmaf(0.5f, tanh_fast(0.851f * x), 0.5f); }
-SC_DEVINL float qgelu_grad_fast(float x) {
-  const float s = fmaf(0.5f, tanh_fast(0.851f * x), 0.5f);
-  return s * fmaf(1.702f * x, 1.0f - s, 1.0f);
-}
-SC_DEVINL void sts128(uint32_t addr, float a, float b, float c, float d) {
-  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
-}
-SC_DEVINL float4 lds128(uint32_t addr) {
-  float4 v;
-  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
-  return v;
-}
-SC_DEVINL uint2 pack4_bf16(const float4& v) {
-  __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y), b = __floats2bfloat162_rn(v.z, v.w);
-  uint2 u;
-  u.x = *(uint32_t*)&a;
-  u.y = *(uint32_t*)&b;
-  return u;
-}
-
-template <int F>
-SC_DEVINL void epi4_fast(const EpiParams& p, int m, int n, float4 v, const float4& b4, const float4& pre) {
-  if constexpr (F == EF_GENERIC) {
-    epi_store4(p, m, n, v);
-  } else {
-    const long off = (long)m * p.ldc + n;
-    if constexpr ((F & EF_BIAS) != 0) { v.x += b4.x; v.y += b4.y; v.z += b4.z; v.w += b4.w; }
-    if constexpr ((F & EF_C2) != 0) *(uint2*)((bf16*)p.C2 + off) = pack4_bf16(v);
-    if constexpr ((F & EF_QGELU) != 0) { v.x = qgelu_fast(v.x); v.y = qgelu_fast(v.y); v.z = qgelu_fast(v.z); v.w = qgelu_fast(v.w); }
-    if constexpr ((F & EF_MULAUX_QGELU) != 0) {
-      const uint32_t ux = __float_as_uint(pre.x), uy = __float_as_uint(pre.y);   // prefetched bf16x4
-      const float2 a = __bfloat1622float2(*(const __nv_bfloat162*)&ux), b = __bfloat1622float2(*(const __nv_bfloat162*)&uy);
-      v.x *= qgelu_grad_fast(a.x); v.y *= qgelu_grad_fast(a.y); v.z *= qgelu_grad_fast(b.x); v.w *= qgelu_grad_fast(b.y);
-    }
-    if constexpr ((F & EF_RESID) != 0) {
-      v.x += pre.x; v.y += pre.y; v.z += pre.z; v.w += pre.w;    // prefetched residual
-    }
-    if constexpr ((F & EF_ATOMIC) != 0) {
-      float* c = (float*)p.C + off;
-      atomicAdd(c, v.x); atomicAdd(c + 1, v.y); atomicAdd(c + 2, v.z); atomicAdd(c + 3, v.w);
-    } else if constexpr ((F & EF_OUT_F32) != 0) {
-      *(float4*)((float*)p.C + off) = v;
-    } else {
-      *(uint2*)((bf16*)p.C + off) = pack4_bf16(v);
+// bf16 2-D tensor map, 128B swizzle, zero fill.  dim0 is the contiguous dimension.
+int sc_get_tensor_map(const void* ptr, uint64_t dim0, uint64_t dim1, uint64_t stride_elems, uint32_t box0, uint32_t box1,
+                   CUtensorMap* out) {
+  static std::mutex mu;
+  static std::unordered_map<MapKey, CUtensorMap, MapKeyHash> cache;
+  MapKey key{ptr, dim0, dim1, stride_elems, box0, box1};
+  {
+    std::lock_guard<std::mutex> g(mu);
+    auto it = cache.find(key);
+    if (it != cache.end()) {
+      *out = it->second;
+      return SC_OK;
     }
   }
+  EncodeTiledFn enc = get_encode_fn();
+  if (!enc) {
+    sc_set_error("cuTensorMapEncodeTiled not available from the CUDA driver");
+    return SC_ERR_CUDA;
+  }
+  cuuint64_t gdim[2] = {dim0, dim1};
+  cuuint64_t gstride[1] = {stride_elems * 2};
+  cuuint32_t box[2] = {box0, box1};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), gdim, gstride, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    sc_set_error("cuTensorMapEncodeTiled failed (%d): ptr=%p dims=(%llu,%llu) stride=%llu box=(%u,%u)", (int)r, ptr,
+                 (unsigned long long)dim0, (unsigned long long)dim1, (unsigned long long)stride_elems, box0, box1);
+    return SC_ERR_CUDA;
+  }
+  std::lock_guard<std::mutex> g(mu);
+  if (cache.size() > 65536) cache.clear();
+  cache[key] = *out;
+  return SC_OK;
 }
 
-// Shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout), SWIZZLE_128B.
-//   K-major : rows of 128 B, 8-row swizzle atoms 1024 B apart (SBO); LBO unused (1).
-//   MN-major: 64-element (128 B) MN chunks; k rows 128 B apart, 8-k-row atoms SBO=1024 B apart,
-//             consecutive MN chunks LBO = 64 rows * 128 B = 8192 B apart (one TMA box each).
-template <bool MN_MAJOR>
-SC_DEVINL uint64_t make_smem_desc(uint32_t smem_addr) {
-  uint64_t d = 0;
-  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
-  d |= (uint64_t)(MN_MAJOR ? (8192 >> 4) : 1) << 16;
-  d |= (uint64_t)(1024 >> 4) << 32;
-  d |= (uint64_t)1 << 46;  // descriptor version (Blackwell)
-  d |= (uint64_t)2 << 61;  // SWIZZLE_128B
-  return d;
+
+// Picks the compile-time specialised epilogue (tc::EF_*) for a descriptor, or EF_GENERIC.
+int sc_select_epilogue(const sc_gemm_desc* d, int splits) {
+  using namespace tc;
+  int ef = EF_GENERIC;
+  const bool simple = d->alpha == 1.0f && !d->rowbias && (!d->accumulate || splits > 1);
+  if (simple) {
+    const bool bias = d->bias != nullptr, resid = d->residual != nullptr, c2 = d->C2 != nullptr, aux = d->mul_aux != nullptr;
+    const bool out_bf16 = d->c_dtype == SC_BF16;
+    if (splits > 1) {
+      if (!bias && !resid && !c2 && !aux && d->act == SC_ACT_NONE) ef = EF_ATOMIC | EF_OUT_F32;
+    } else if (!aux && !c2 && !resid && d->act == SC_ACT_NONE && out_bf16) {
+      ef = bias ? EF_BIAS : 0;
+    } else if (bias && c2 && d->c2_dtype == SC_BF16 && out_bf16 && d->act == SC_ACT_QUICKGELU && !resid && !aux) {
+      ef = EF_BIAS | EF_QGELU | EF_C2;
+    } else if (bias && resid && !c2 && !aux && d->act == SC_ACT_NONE && !out_bf16) {
+      ef = EF_BIAS | EF_RESID | EF_OUT_F32;
+    } else if (aux && d->mul_aux_dtype == SC_BF16 && d->mul_aux_act == SC_ACT_QUICKGELU && !bias && !resid && !c2 &&
+               d->act == SC_ACT_NONE && out_bf16) {
+      ef = EF_MULAUX_QGELU;
+    }
+  }
+  return ef;
 }
+
+namespace {
+using namespace tc;
 
 template <int BN>
 struct TileCfg {
@@ -377,82 +325,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   }
 }
 
-// ---------------------------------------------------------------------------------------------
-// host side: tensor-map cache + dispatch
-// ---------------------------------------------------------------------------------------------
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
-                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-EncodeTiledFn get_encode_fn() {
-  static EncodeTiledFn fn = nullptr;
-  static std::once_flag once;
-  std::call_once(once, [] {
-    void* p = nullptr;
-    cudaDriverEntryPointQueryResult q;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
-        q == cudaDriverEntryPointSuccess)
-      fn = (EncodeTiledFn)p;
-  });
-  return fn;
-}
-
-struct MapKey {
-  const void* ptr;
-  uint64_t d0, d1, stride;
-  uint32_t b0, b1;
-  bool operator==(const MapKey& o) const {
-    return ptr == o.ptr && d0 == o.d0 && d1 == o.d1 && stride == o.stride && b0 == o.b0 && b1 == o.b1;
-  }
-};
-struct MapKeyHash {
-  size_t operator()(const MapKey& k) const {
-    size_t h = (size_t)k.ptr;
-    h = h * 1000003u ^ k.d0;
-    h = h * 1000003u ^ k.d1;
-    h = h * 1000003u ^ k.stride;
-    h = h * 1000003u ^ ((uint64_t)k.b0 << 32 | k.b1);
-    return h;
-  }
-};
-
-// bf16 2-D tensor map, 128B swizzle, zero fill.  dim0 is the contiguous dimension.
-int get_tensor_map(const void* ptr, uint64_t dim0, uint64_t dim1, uint64_t stride_elems, uint32_t box0, uint32_t box1,
-                   CUtensorMap* out) {
-  static std::mutex mu;
-  static std::unordered_map<MapKey, CUtensorMap, MapKeyHash> cache;
-  MapKey key{ptr, dim0, dim1, stride_elems, box0, box1};
-  {
-    std::lock_guard<std::mutex> g(mu);
-    auto it = cache.find(key);
-    if (it != cache.end()) {
-      *out = it->second;
-      return SC_OK;
-    }
-  }
-  EncodeTiledFn enc = get_encode_fn();
-  if (!enc) {
-    sc_set_error("cuTensorMapEncodeTiled not available from the CUDA driver");
-    return SC_ERR_CUDA;
-  }
-  cuuint64_t gdim[2] = {dim0, dim1};
-  cuuint64_t gstride[1] = {stride_elems * 2};
-  cuuint32_t box[2] = {box0, box1};
-  cuuint32_t estr[2] = {1, 1};
-  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), gdim, gstride, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS) {
-    sc_set_error("cuTensorMapEncodeTiled failed (%d): ptr=%p dims=(%llu,%llu) stride=%llu box=(%u,%u)", (int)r, ptr,
-                 (unsigned long long)dim0, (unsigned long long)dim1, (unsigned long long)stride_elems, box0, box1);
-    return SC_ERR_CUDA;
-  }
-  std::lock_guard<std::mutex> g(mu);
-  if (cache.size() > 65536) cache.clear();
-  cache[key] = *out;
-  return SC_OK;
-}
-
 template <int BN, bool A_MN, bool B_MN, int EF>
 int launch(const sc_gemm_desc* d, const CUtensorMap& ta, const CUtensorMap& tb, int splits, cudaStream_t st) {
   using Cfg = TileCfg<BN>;
@@ -479,6 +351,7 @@ int launch(const sc_gemm_desc* d, const CUtensorMap& ta, const CUtensorMap& tb, 
 }  // namespace
 
 extern void sc_count_launch(int n);
+int sc_gemm_tc2(const sc_gemm_desc* d, cudaStream_t st);
 
 // Returns SC_ERR_UNSUPPORTED when the problem does not meet the TMA alignment rules (caller falls
 // back to the FMA kernel only in fp32 mode; in bf16 mode this is an error).
@@ -493,6 +366,13 @@ int sc_gemm_tc(const sc_gemm_desc* d, cudaStream_t st) {
                  "(M=%d N=%d K=%d lda=%lld ldb=%lld ldc=%lld)", d->M, d->N, d->K, (long long)d->lda,
                  (long long)d->ldb, (long long)d->ldc);
     return SC_ERR_UNSUPPORTED;
+  }
+  {
+    static const int use_2cta = [] { const char* e = getenv("SC_GEMM_2CTA"); return e ? atoi(e) : 1; }();
+    if (use_2cta) {
+      const int rc2 = sc_gemm_tc2(d, st);
+      if (rc2 != SC_ERR_UNSUPPORTED) return rc2;
+    }
   }
   const int waste256 = ceil_div(d->N, 256) * 256 - d->N, waste128 = ceil_div(d->N, 128) * 128 - d->N;
   const int BN = (waste256 <= waste128) ? 256 : 128;
@@ -513,32 +393,14 @@ int sc_gemm_tc(const sc_gemm_desc* d, cudaStream_t st) {
 
   CUtensorMap ta, tb;
   int rc;
-  if (!a_mn) rc = get_tensor_map(d->A, d->K, d->M, d->lda, BK, BM, &ta);
-  else rc = get_tensor_map(d->A, d->M, d->K, d->lda, 64, BK, &ta);
+  if (!a_mn) rc = sc_get_tensor_map(d->A, d->K, d->M, d->lda, BK, BM, &ta);
+  else rc = sc_get_tensor_map(d->A, d->M, d->K, d->lda, 64, BK, &ta);
   if (rc) return rc;
-  if (!b_mn) rc = get_tensor_map(d->B, d->K, d->N, d->ldb, BK, BN, &tb);
-  else rc = get_tensor_map(d->B, d->N, d->K, d->ldb, 64, BK, &tb);
+  if (!b_mn) rc = sc_get_tensor_map(d->B, d->K, d->N, d->ldb, BK, BN, &tb);
+  else rc = sc_get_tensor_map(d->B, d->N, d->K, d->ldb, 64, BK, &tb);
   if (rc) return rc;
 
-  // epilogue specialisation
-  int ef = EF_GENERIC;
-  const bool simple = d->alpha == 1.0f && !d->rowbias && (!d->accumulate || splits > 1);
-  if (simple) {
-    const bool bias = d->bias != nullptr, resid = d->residual != nullptr, c2 = d->C2 != nullptr, aux = d->mul_aux != nullptr;
-    const bool out_bf16 = d->c_dtype == SC_BF16;
-    if (splits > 1) {
-      if (!bias && !resid && !c2 && !aux && d->act == SC_ACT_NONE) ef = EF_ATOMIC | EF_OUT_F32;
-    } else if (!aux && !c2 && !resid && d->act == SC_ACT_NONE && out_bf16) {
-      ef = bias ? EF_BIAS : 0;
-    } else if (bias && c2 && d->c2_dtype == SC_BF16 && out_bf16 && d->act == SC_ACT_QUICKGELU && !resid && !aux) {
-      ef = EF_BIAS | EF_QGELU | EF_C2;
-    } else if (bias && resid && !c2 && !aux && d->act == SC_ACT_NONE && !out_bf16) {
-      ef = EF_BIAS | EF_RESID | EF_OUT_F32;
-    } else if (aux && d->mul_aux_dtype == SC_BF16 && d->mul_aux_act == SC_ACT_QUICKGELU && !bias && !resid && !c2 &&
-               d->act == SC_ACT_NONE && out_bf16) {
-      ef = EF_MULAUX_QGELU;
-    }
-  }
+  const int ef = sc_select_epilogue(d, splits);
   sc_count_launch(1);
 #define SC_L(BN_, A_, B_, EF_) return launch<BN_, A_, B_, EF_>(d, ta, tb, splits, st);
 #define SC_DISPATCH(BN_)                                                                     \

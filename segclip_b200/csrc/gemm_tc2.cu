@@ -1,0 +1,313 @@
+// 2-CTA tcgen05 GEMM (cta_group::2): a pair of SMs computes one 256 x 256 tile.
+//
+// Each CTA of the cluster stages its 128 rows of A and its 128-row half of B (32 KB per stage instead of 48 KB for a
+// 128 x 256 tile), so L2 -> SM operand traffic per FLOP drops by 1.5x and the smem ring is 6 deep.  The leader CTA issues
+// tcgen05.mma.cta_group::2 (M = 256, N = 256, K = 16); every CTA keeps its own 128 x 256 accumulator in its TMEM
+// (two buffers) and runs its own epilogue.  Synchronisation:
+//   full[stage]  (leader's): both CTAs' TMA loads complete_tx on the leader's barrier (peer bit cleared)
+//   empty[stage] (both)    : tcgen05.commit ... multicast::cluster 0b11 from the leader's MMA thread
+//   tmem_full[acc] (both)  : same multicast commit after the last k-block
+//   tmem_empty[acc] (leader's, 16 arrivals): epilogue warps of both CTAs arrive through the cluster window
+// Everything else (operand layouts, split-K, fused epilogues) is identical to gemm_tc.cu.
+#include "gemm_tc_common.cuh"
+
+namespace {
+using namespace tc;
+
+constexpr int STAGES2 = 6;
+constexpr int A2_BYTES = 128 * BK * 2;
+constexpr int B2_BYTES = 128 * BK * 2;
+constexpr int STAGE2_BYTES = A2_BYTES + B2_BYTES;
+constexpr int SMEM2_BYTES = STAGES2 * STAGE2_BYTES + 256 + NUM_EPI_WARPS * 4096;
+constexpr uint32_t PEER_MASK = 0xFEFFFFFFu;   // clears the CTA-rank bit of a shared::cluster address -> CTA 0 of the pair
+
+SC_DEVINL uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+SC_DEVINL void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+SC_DEVINL void tma_load_2d_2sm(const CUtensorMap* map, uint64_t* leader_bar, void* dst, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(dst)), "l"((uint64_t)map), "r"(smem_u32(leader_bar) & PEER_MASK), "r"(c0), "r"(c1)
+      : "memory");
+}
+SC_DEVINL void tcgen05_mma2_f16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accum)
+      : "memory");
+}
+SC_DEVINL void tcgen05_commit2(uint64_t* bar) {   // arrives on the same barrier of both CTAs
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(smem_u32(bar)), "h"((uint16_t)3)
+               : "memory");
+}
+SC_DEVINL void mbar_arrive_leader(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(smem_u32(bar) & PEER_MASK) : "memory");
+}
+
+template <bool A_MN, bool B_MN, int EF>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
+gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int tiles_m, int tiles_n,
+                int splits, int kb_total, int kb_per_split, EpiParams ep) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  if ((smem_u32(smem) & 1023u) != 0u) __trap();
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + STAGES2 * A2_BYTES;
+  uint64_t* bars = (uint64_t*)(smem + STAGES2 * STAGE2_BYTES);
+  uint64_t* full_bar = bars;
+  uint64_t* empty_bar = bars + STAGES2;
+  uint64_t* tmem_full = bars + 2 * STAGES2;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint32_t* tmem_slot = (uint32_t*)(tmem_empty + 2);
+  uint8_t* epi_stage = smem + STAGES2 * STAGE2_BYTES + 256;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < STAGES2; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tmem_full[i], 1);
+      mbar_init(&tmem_empty[i], 2 * NUM_EPI_WARPS);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  if (warp == NUM_EPI_WARPS + 1) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tcgen05_fence_before();
+  cluster_sync_all();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const int num_items = tiles_m * tiles_n * splits;
+
+  if (warp == NUM_EPI_WARPS) {
+    // =============================== TMA producer (both CTAs) ===============================
+    if (lane == 0) {
+      asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tmA) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tmB) : "memory");
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int item = pair; item < num_items; item += npairs) {
+        const int nt = item % tiles_n;
+        const int mt = (item / tiles_n) % tiles_m;
+        const int sp = item / (tiles_n * tiles_m);
+        const int m0 = mt * 256 + rank * 128, n0 = nt * 256 + rank * 128;
+        const int kb0 = sp * kb_per_split;
+        const int kb1 = min(kb_total, kb0 + kb_per_split);
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          if (rank == 0) mbar_expect_tx(&full_bar[stage], 2 * STAGE2_BYTES);
+          uint8_t* sa = smem_a + stage * A2_BYTES;
+          uint8_t* sb = smem_b + stage * B2_BYTES;
+          if (!A_MN) {
+            tma_load_2d_2sm(&tmA, &full_bar[stage], sa, kb * BK, m0);
+          } else {
+            tma_load_2d_2sm(&tmA, &full_bar[stage], sa, m0, kb * BK);
+            tma_load_2d_2sm(&tmA, &full_bar[stage], sa + 8192, m0 + 64, kb * BK);
+          }
+          if (!B_MN) {
+            tma_load_2d_2sm(&tmB, &full_bar[stage], sb, kb * BK, n0);
+          } else {
+            tma_load_2d_2sm(&tmB, &full_bar[stage], sb, n0, kb * BK);
+            tma_load_2d_2sm(&tmB, &full_bar[stage], sb + 8192, n0 + 64, kb * BK);
+          }
+          if (++stage == STAGES2) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == NUM_EPI_WARPS + 1) {
+    // =============================== MMA issuer (leader CTA only) ===============================
+    if (lane == 0 && rank == 0) {
+      constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((A_MN ? 1u : 0u) << 15) | ((B_MN ? 1u : 0u) << 16) |
+                                 ((uint32_t)(256 >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+      constexpr uint32_t a_kstep = A_MN ? (16 * 128) >> 4 : (16 * 2) >> 4;
+      constexpr uint32_t b_kstep = B_MN ? (16 * 128) >> 4 : (16 * 2) >> 4;
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int item = pair; item < num_items; item += npairs, ++it) {
+        const int sp = item / (tiles_n * tiles_m);
+        const int kb0 = sp * kb_per_split;
+        const int kb1 = min(kb_total, kb0 + kb_per_split);
+        const int acc = it & 1;
+        const uint32_t acc_phase = (it >> 1) & 1;
+        mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+        tcgen05_fence_after();
+        const uint32_t tmem_d = tmem_base + acc * 256;
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tcgen05_fence_after();
+          const uint64_t da = make_smem_desc<A_MN>(smem_u32(smem_a + stage * A2_BYTES));
+          const uint64_t db = make_smem_desc<B_MN>(smem_u32(smem_b + stage * B2_BYTES));
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k)
+            tcgen05_mma2_f16(tmem_d, da + (uint64_t)(k * a_kstep), db + (uint64_t)(k * b_kstep), idesc,
+                             (kb > kb0 || k > 0) ? 1u : 0u);
+          tcgen05_commit2(&empty_bar[stage]);
+          if (++stage == STAGES2) { stage = 0; phase ^= 1; }
+        }
+        tcgen05_commit2(&tmem_full[acc]);
+      }
+    }
+  } else {
+    // =============================== epilogue (both CTAs, own 128 rows) ===============================
+    const int quarter = warp & 3;
+    const int half = warp >> 2;
+    const uint32_t stage = smem_u32(epi_stage) + warp * 4096;
+    const int l7 = lane & 7, l3 = lane >> 3;
+    int it = 0;
+    for (int item = pair; item < num_items; item += npairs, ++it) {
+      const int nt = item % tiles_n;
+      const int mt = (item / tiles_n) % tiles_m;
+      const int nbase = nt * 256 + half * 128;
+      const int acc = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1;
+      mbar_wait(&tmem_full[acc], acc_phase);
+      tcgen05_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * 256 + half * 128;
+      const int mrow0 = mt * 256 + rank * 128 + quarter * 32;
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
+        float v[32];
+        const int n = nbase + c * 32 + l7 * 4;
+        float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        float4 pre[8];
+        if (n < ep.N) {
+          if constexpr (EF != EF_GENERIC && (EF & EF_BIAS) != 0) b4 = __ldg((const float4*)(ep.bias + n));
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int m = mrow0 + 4 * i + l3;
+            pre[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if constexpr (EF != EF_GENERIC && (EF & EF_RESID) != 0) {
+              if (m < ep.M) pre[i] = *(const float4*)(ep.residual + (long)m * ep.ldr + n);
+            }
+            if constexpr (EF != EF_GENERIC && (EF & EF_MULAUX_QGELU) != 0) {
+              if (m < ep.M) {
+                const uint2 u = *(const uint2*)((const bf16*)ep.mul_aux + (long)m * ep.ldc + n);
+                pre[i].x = __uint_as_float(u.x);
+                pre[i].y = __uint_as_float(u.y);
+              }
+            }
+          }
+        }
+        tmem_ld32(taddr + c * 32, v);
+        __syncwarp();
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          sts128(stage + lane * 128 + ((j ^ l7) << 4), v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+        __syncwarp();
+        if (n < ep.N) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int r = 4 * i + l3;
+            const float4 x = lds128(stage + r * 128 + ((l7 ^ (r & 7)) << 4));
+            const int m = mrow0 + r;
+            if (m < ep.M) epi4_fast<EF>(ep, m, n, x, b4, pre[i]);
+          }
+        }
+      }
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_leader(&tmem_empty[acc]);
+    }
+  }
+
+  tcgen05_fence_before();
+  cluster_sync_all();
+  if (warp == NUM_EPI_WARPS + 1) {
+    tcgen05_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+  }
+}
+
+template <bool A_MN, bool B_MN, int EF>
+int launch2(const sc_gemm_desc* d, const CUtensorMap& ta, const CUtensorMap& tb, int splits, cudaStream_t st) {
+  auto kern = gemm_tc2_kernel<A_MN, B_MN, EF>;
+  static bool configured = false;
+  if (!configured) {
+    SC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM2_BYTES));
+    configured = true;
+  }
+  const int tiles_m = ceil_div(d->M, 256), tiles_n = ceil_div(d->N, 256);
+  const int kb_total = ceil_div(d->K, BK);
+  int kb_per = ceil_div(kb_total, splits);
+  splits = ceil_div(kb_total, kb_per);
+  sc_gemm_desc dd = *d;
+  dd.split_k = splits;
+  EpiParams ep = make_epi(&dd);
+  const int items = tiles_m * tiles_n * splits;
+  const int max_pairs = sc_num_sms() / 2;
+  const int pairs = items < max_pairs ? items : max_pairs;
+  kern<<<2 * pairs, NUM_THREADS, SMEM2_BYTES, st>>>(ta, tb, tiles_m, tiles_n, splits, kb_total, kb_per, ep);
+  SC_LAUNCH_CHECK();
+  return SC_OK;
+}
+
+}  // namespace
+
+extern void sc_count_launch(int n);
+
+// Same contract as sc_gemm_tc; the caller has already validated alignment.  Returns SC_ERR_UNSUPPORTED when the shape is
+// a poor fit for 256 x 256 pair tiles (the 1-CTA kernel then runs).
+int sc_gemm_tc2(const sc_gemm_desc* d, cudaStream_t st) {
+  using namespace tc;
+  const bool a_mn = d->trans_a != 0, b_mn = d->trans_b != 0;
+  if (d->M < 512 || d->N < 256 || (a_mn && !b_mn)) return SC_ERR_UNSUPPORTED;
+  const int waste = ceil_div(d->N, 256) * 256 - d->N;
+  if (waste * 8 > d->N) return SC_ERR_UNSUPPORTED;       // > 12.5 % padded columns: 128-wide tiles fit better
+  const int kb_total = ceil_div(d->K, BK);
+  int splits = d->split_k;
+  if (splits < 0) {
+    const int tiles = ceil_div(d->M, 256) * ceil_div(d->N, 256);
+    splits = (2 * (sc_num_sms() / 2) + tiles - 1) / tiles;
+    if (splits > kb_total / 4) splits = kb_total / 4;
+  }
+  if (splits < 1) splits = 1;
+  if (splits > kb_total) splits = kb_total;
+  if (splits > 1 && !(d->accumulate && d->c_dtype == SC_F32 && !d->C2)) {
+    sc_set_error("sc_gemm: split_k > 1 requires accumulate=1 into an fp32 C and no C2");
+    return SC_ERR_INVALID;
+  }
+  CUtensorMap ta, tb;
+  int rc;
+  if (!a_mn) rc = sc_get_tensor_map(d->A, d->K, d->M, d->lda, BK, 128, &ta);
+  else rc = sc_get_tensor_map(d->A, d->M, d->K, d->lda, 64, BK, &ta);
+  if (rc) return rc;
+  if (!b_mn) rc = sc_get_tensor_map(d->B, d->K, d->N, d->ldb, BK, 128, &tb);
+  else rc = sc_get_tensor_map(d->B, d->N, d->K, d->ldb, 64, BK, &tb);
+  if (rc) return rc;
+  const int ef = sc_select_epilogue(d, splits);
+  sc_count_launch(1);
+#define SC_L2(A_, B_, EF_) return launch2<A_, B_, EF_>(d, ta, tb, splits, st);
+  if (!a_mn && !b_mn) {
+    if (ef == EF_BIAS) SC_L2(false, false, EF_BIAS)
+    if (ef == 0) SC_L2(false, false, 0)
+    if (ef == (EF_BIAS | EF_QGELU | EF_C2)) SC_L2(false, false, EF_BIAS | EF_QGELU | EF_C2)
+    if (ef == (EF_BIAS | EF_RESID | EF_OUT_F32)) SC_L2(false, false, EF_BIAS | EF_RESID | EF_OUT_F32)
+    SC_L2(false, false, EF_GENERIC)
+  }
+  if (!a_mn && b_mn) {
+    if (ef == 0) SC_L2(false, true, 0)
+    if (ef == EF_MULAUX_QGELU) SC_L2(false, true, EF_MULAUX_QGELU)
+    SC_L2(false, true, EF_GENERIC)
+  }
+  if (ef == (EF_ATOMIC | EF_OUT_F32)) SC_L2(true, true, EF_ATOMIC | EF_OUT_F32)
+  SC_L2(true, true, EF_GENERIC)
+#undef SC_L2
+}
