@@ -135,6 +135,7 @@ def main():
     ap.add_argument("--cpu-batch", type=int, default=16)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--precision", default="bf16")
+    ap.add_argument("--ddp", action="store_true", help="use torch DDP for the gradient mean instead of the native overlapped sync")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl != "reference" else args.warmup
     if args.impl == "reference":
@@ -164,8 +165,11 @@ def main():
     if world > 1:
         from segclip_b200.p2p import EmbeddingExchange
         model.attach_exchange(EmbeddingExchange(dist.group.WORLD, dev))
-        net = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local], find_unused_parameters=True,
-                                                        gradient_as_bucket_view=True)
+        if args.ddp:          # comparator: stock DistributedDataParallel hooks (all-reduce after the native backward)
+            net = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local], find_unused_parameters=True,
+                                                            gradient_as_bucket_view=True)
+        else:                 # product path: bucketed all-reduce overlapped inside the native backward tape
+            model.enable_native_grad_sync(dist.group.WORLD)
     B = args.batch
     host = synthetic_batch(cfg, B, 0, rank, args.heads)
     pinned = {k: v.pin_memory() for k, v in host.items()}
@@ -221,7 +225,7 @@ def main():
         "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
         "data": "synthetic",
         "config": {"workload": workload_name(args), "per_gpu_batch": B, "global_batch": B * world,
-                   "parallelism": "dp%d" % world, "l2": "per-step working set (GBs of activations) exceeds the 126 MB L2"},
+                   "parallelism": "dp%d" % world, "grad_sync": ("ddp" if args.ddp else "native-overlapped") if world > 1 else "none", "l2": "per-step working set (GBs of activations) exceeds the 126 MB L2"},
         "e2e": {"value": B * world / (ms_e2e / 1e3), "unit": "pairs/s",
                 "h2d_bytes_per_step": int(host["input_ids"].numel() * 8 + host["image"].numel() * 4 +
                                           (host["image_seg"].numel() * 8 if args.heads else 0)),

@@ -96,20 +96,13 @@ class Engine:
         self._ptr_sig = None
         self._setup_params()
         self.gather = None        # multi-GPU embedding exchange (segclip_b200.p2p), set by the module
+        self.sync_group = None    # native gradient all-reduce (enable_grad_sync)
+        self.sync_world = 1
 
     # ------------------------------------------------------------------ parameters
     def _setup_params(self):
         dev = self.dev
-        names = [n for n in self.params if n not in FROZEN_STEM]
-        self.grad_names = names
-        sizes = [self.params[n].numel() for n in names]
-        offs, tot = [], 0
-        for s in sizes:
-            offs.append(tot)
-            tot += (s + 3) // 4 * 4          # keep every view 16-byte aligned
-        self.gflat = torch.zeros(tot, device=dev, dtype=torch.float32)
-        self.goffs = dict(zip(names, offs))
-        self.grads = {n: self.gflat[o:o + s].view(self.params[n].shape) for n, o, s in zip(names, offs, sizes)}
+        self._layout_grads([n for n in self.params if n not in FROZEN_STEM])
         self._sig()
         # compute-dtype shadows of the GEMM weights (bf16 mode); fp32 mode reads the masters directly
         self.shadow = {}
@@ -144,6 +137,51 @@ class Engine:
         self.prep_ops = [ops.blockdiag_expand_op(self.params[s + "k_conv.weight"].data, self.kdense, self.Hv),
                          ops.blockdiag_expand_op(self.params[s + "v_conv.weight"].data, self.vdense, self.Hv)]
 
+    def _layout_grads(self, names):
+        """One flat fp32 gradient buffer; `names` fixes the order (backward-completion order when the native
+        gradient all-reduce is enabled, so finished prefixes can be reduced while backward continues)."""
+        self.grad_names = list(names)
+        sizes = [self.params[n].numel() for n in names]
+        offs, tot = [], 0
+        for s in sizes:
+            offs.append(tot)
+            tot += (s + 3) // 4 * 4          # keep every view 16-byte aligned
+        if getattr(self, "gflat", None) is None or self.gflat.numel() != tot:
+            self.gflat = torch.zeros(tot, device=self.dev, dtype=torch.float32)
+        self.goffs = dict(zip(names, offs))
+        self.gsizes = dict(zip(names, sizes))
+        self.grads = {n: self.gflat[o:o + s].view(self.params[n].shape) for n, o, s in zip(names, offs, sizes)}
+
+    # ------------------------------------------------------------------ native gradient all-reduce
+    def enable_grad_sync(self, group, bucket_mb=48):
+        """Bucketed NCCL all-reduce of the flat gradient buffer, launched from inside the backward tape as soon as a
+        prefix of the buffer is final (replaces DDP's hooks, main_task_align.py:251-252: the native backward is a single
+        autograd node, so DDP could only reduce after it).  The mean (1/world) is folded into the final hand-over."""
+        assert not self.plans, "enable_grad_sync must be called before the first forward"
+        import torch.distributed as dist
+        self.sync_group = group
+        self.sync_world = dist.get_world_size(group)
+        # dry run on a tiny batch: find, for every parameter, the last backward op that writes its gradient
+        probe = self._build(2, probe=True)
+        last = {n: -1 for n in self.grad_names}
+        last.update(self._last_writers(probe))
+        del probe
+        order = sorted(self.grad_names, key=lambda n: (last[n], self.goffs[n]))
+        self._grad_last_op = last
+        self._layout_grads(order)
+        # buckets over the new order
+        limit = bucket_mb * (1 << 20) // 4
+        self.buckets = []          # (start, end, name of last param)
+        start = 0
+        for n in order:
+            end = self.goffs[n] + (self.gsizes[n] + 3) // 4 * 4
+            if end - start >= limit:
+                self.buckets.append((start, end, n))
+                start = end
+        if start < self.gflat.numel():
+            self.buckets.append((start, self.gflat.numel(), order[-1]))
+        self.plans = {}
+
     def _sig(self):
         self._ptr_sig = tuple(p.data_ptr() for p in self.params.values())
 
@@ -168,7 +206,7 @@ class Engine:
             self.plans[B] = self._build(B)
         return self.plans[B]
 
-    def _build(self, B):
+    def _build(self, B, probe=False):
         pl = Plan()
         dev, T = self.dev, self.T
         f32, i32 = torch.float32, torch.int32
@@ -469,7 +507,7 @@ class Engine:
         # =============================================================== contrastive head
         # (modules/modeling.py:204-209,338-357)
         N = B * self.world
-        if self.world > 1:
+        if self.world > 1 and not probe:
             if self.gather is None:
                 raise L.SegclipB200Error("world_size > 1: attach an exchange (segclip_b200.p2p.EmbeddingExchange) first")
             t_all, v_all, lse_ext = self.gather.buffers(B, self.E)
@@ -485,7 +523,7 @@ class Engine:
         raw_t2v, raw_v2t = buf("c.t2v", (B, N)), buf("c.v2t", (B, N))
         pl.f(ops.gemm_op(t_n, v_all, raw_t2v))
         pl.f(ops.gemm_op(v_n, t_all, raw_v2t))
-        if self.world > 1:
+        if self.world > 1 and not probe:
             lse_all = lse_ext
             pl.bufs["c.lse_all"] = lse_all
         else:
@@ -569,7 +607,49 @@ class Engine:
         pl.finish()
         pl.scratch = scratch
         pl.loss = loss
+        pl.bucket_after = {}
+        if self.sync_group is not None and not probe:
+            # op index after which each bucket is final = last writer of its last-finishing parameter
+            names_by_bucket = []
+            for (s, e_, _) in self.buckets:
+                names_by_bucket.append([n for n in self.grad_names if s <= self.goffs[n] < e_])
+            lo, hi = self.gflat.data_ptr(), self.gflat.data_ptr() + self.gflat.numel() * 4
+            last = self._last_writers(pl)
+            for k, names in enumerate(names_by_bucket):
+                idx = max([last.get(n, -1) for n in names] + [-1])
+                pl.bucket_after.setdefault(idx, []).append(k)
         return pl
+
+    def _last_writers(self, pl):
+        import bisect
+        lo, hi = self.gflat.data_ptr(), self.gflat.data_ptr() + self.gflat.numel() * 4
+        starts = sorted((self.goffs[n], n) for n in self.grad_names)
+        keys = [s for s, _ in starts]
+        last = {}
+
+        def tensors(obj):
+            if isinstance(obj, torch.Tensor):
+                yield obj
+            elif isinstance(obj, (tuple, list)):
+                for o in obj:
+                    yield from tensors(o)
+            elif isinstance(obj, dict):
+                for o in obj.values():
+                    yield from tensors(o)
+
+        for i, op in enumerate(pl.bwd):
+            if isinstance(op, str):
+                continue
+            for t in tensors(op.keep):
+                p = t.data_ptr()
+                if lo <= p < hi:
+                    off = (p - lo) // 4
+                    end = off + (t.numel() if t.is_contiguous() else 1)
+                    j = bisect.bisect_right(keys, off) - 1
+                    while j < len(starts) and starts[j][0] < end:
+                        last[starts[j][1]] = i
+                        j += 1
+        return last
 
     # ------------------------------------------------------------------ execution
     def forward(self, B, inputs, noise, forced=None):
@@ -614,11 +694,23 @@ class Engine:
     def backward(self, B):
         pl = self.plan(B)
         st = L.stream()
-        for op in pl.bwd:
+        works = []
+        if pl.bucket_after:
+            import torch.distributed as dist
+            for k in pl.bucket_after.get(-1, []):          # parameters nobody writes (stay zero)
+                s, e_, _ = self.buckets[k]
+                works.append(dist.all_reduce(self.gflat[s:e_], group=self.sync_group, async_op=True))
+        for i, op in enumerate(pl.bwd):
             if isinstance(op, str):
                 self._collective(op, pl)
             else:
                 op(st)
+            if pl.bucket_after and i in pl.bucket_after:
+                for k in pl.bucket_after[i]:
+                    s, e_, _ = self.buckets[k]
+                    works.append(dist.all_reduce(self.gflat[s:e_], group=self.sync_group, async_op=True))
+        for w in works:
+            w.wait()               # stream-level wait, the host does not block
         return self.gflat
 
     def profile_gemm(self, B):

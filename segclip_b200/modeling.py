@@ -201,6 +201,8 @@ class _NativeStep(torch.autograd.Function):
         gflat = eng.backward(ctx.B)
         out = torch.empty_like(gflat)
         scale = gout.detach().to(torch.float32).contiguous().view(1)
+        if eng.sync_world > 1:
+            scale = scale / eng.sync_world          # mean over ranks, folded into the hand-over copy
         ops.convert_op(gflat, out, scale)()          # grad * grad_output, read on the device
         grads = []
         for name, p in owner._active_items:
@@ -249,6 +251,7 @@ class SegCLIP(nn.Module):
         self._noise = None
         self._forced = None
         self._exchange = None
+        self._sync_group = None
 
     # ---- reference-compatible constructors ---------------------------------------------------
     @classmethod
@@ -306,6 +309,10 @@ class SegCLIP(nn.Module):
                                   if n in self._engine.grads and n not in self._untouched]
             if self._exchange is not None:
                 self._engine.gather = self._exchange
+            if self._sync_group is not None:
+                self._engine.enable_grad_sync(self._sync_group)
+                self._active_items = [(n, p) for n, p in named.items()
+                                      if n in self._engine.grads and n not in self._untouched]
         return self._engine
 
     def attach_exchange(self, exchange):
@@ -313,6 +320,12 @@ class SegCLIP(nn.Module):
         self._exchange = exchange
         if self._engine is not None:
             self._engine.gather = exchange
+
+    def enable_native_grad_sync(self, group):
+        """Average gradients across `group` inside the native backward (bucketed NCCL all-reduce overlapped with the
+        remaining backward kernels).  Use INSTEAD of DistributedDataParallel, before the first forward."""
+        assert self._engine is None, "call before the first forward"
+        self._sync_group = group
 
     def inject_noise(self, noise):
         """Replay explicit uniform draws {u1,u2,u3} instead of torch.rand (parity tests)."""

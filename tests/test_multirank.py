@@ -51,7 +51,7 @@ def test_collective_exchange_gloo_world2():
 
 def _gpu_worker(rank, world, port, mode, q):
     os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
-    os.environ["SEGCLIP_EXCHANGE"] = mode
+    os.environ["SEGCLIP_EXCHANGE"] = "nccl" if mode == "nccl" else "p2p"
     torch.cuda.set_device(rank)
     dev = torch.device("cuda", rank)
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
@@ -68,6 +68,8 @@ def _gpu_worker(rank, world, port, mode, q):
     model.load_state_dict(so.init_params(cfg, seed=g["param_seed"]), strict=False)
     model = model.to(dev).train()
     model.attach_exchange(EmbeddingExchange(dist.group.WORLD, dev))
+    if mode == "native":                    # gradient mean inside the native backward (overlapped bucketed all-reduce)
+        model.enable_native_grad_sync(dist.group.WORLD)
     batch, noise = so.make_batch(cfg, g["batch"], seed=g["batch_seed"], rank=rank)
     model.inject_noise({k: v.to(dev) for k, v in noise.items()})
     ids = batch["input_ids"]
@@ -81,8 +83,10 @@ def _gpu_worker(rank, world, port, mode, q):
     for n, p in model.named_parameters():
         if p.grad is not None:
             gr = p.grad.detach().clone()
-            dist.all_reduce(gr)
-            grads[n] = (gr / world).cpu()
+            if mode != "native":
+                dist.all_reduce(gr)
+                gr = gr / world
+            grads[n] = gr.cpu()
     bad = compare_grads(grads, g["grads"], tol=1e-3, skip=FROZEN_STEM) if rank == 0 else []
     q.put((rank, losses, g["loss"][rank], bad[:5]))
     dist.barrier()
@@ -90,13 +94,13 @@ def _gpu_worker(rank, world, port, mode, q):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("mode", ["p2p", "nccl"])
+@pytest.mark.parametrize("mode", ["p2p", "nccl", "native"])
 def test_two_ranks_match_reference_fixture(mode):
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs (gpurun --gpus 2)")
     ctx = mp.get_context("spawn")
     q = ctx.SimpleQueue()
-    port = 29571 if mode == "p2p" else 29573
+    port = {"p2p": 29571, "nccl": 29573, "native": 29575}[mode]
     procs = [ctx.Process(target=_gpu_worker, args=(r, 2, port, mode, q)) for r in range(2)]
     for p in procs:
         p.start()
