@@ -13,6 +13,7 @@ SHAPES = [  # name, M, N, K, ta, tb, kwargs
     ("c_fc     fwd", 50176, 3072, 768, False, False, dict(bias=True, act=1, c2=True, out=torch.bfloat16)),
     ("c_proj   fwd", 50176, 768, 3072, False, False, dict(bias=True, residual=True, out=torch.float32)),
     ("c_proj dgrad", 50176, 3072, 768, False, True, dict(out=torch.bfloat16)),
+    ("c_proj dgrad*", 50176, 3072, 768, False, True, dict(out=torch.bfloat16, aux=True)),
     ("c_fc   dgrad", 50176, 768, 3072, False, True, dict(out=torch.bfloat16)),
     ("c_fc   wgrad", 3072, 768, 50176, True, True, dict(acc=True, out=torch.float32)),
     ("c_proj wgrad", 768, 3072, 50176, True, True, dict(acc=True, out=torch.float32)),
@@ -31,7 +32,9 @@ def main():
         bias = torch.randn(N, device=dev) if kw.get("bias") else None
         res = torch.randn(M, N, device=dev) if kw.get("residual") else None
         C2 = torch.empty(M, N, device=dev, dtype=kw["out"]) if kw.get("c2") else None
+        aux = torch.randn(M, N, device=dev).bfloat16() if kw.get("aux") else None
         op = ops.gemm_op(A, B, C, trans_a=ta, trans_b=tb, bias=bias, residual=res, act=kw.get("act", 0), C2=C2,
+                         mul_aux=aux, mul_aux_act=1 if aux is not None else 0,
                          accumulate=kw.get("acc", False), split_k=-1 if kw.get("acc") else 0)
         for _ in range(3):
             op()
