@@ -8,6 +8,8 @@
 // One CTA per (head, batch slot); K and V (fwd, dQ pass) or Q and dO (dK/dV pass) staged once in
 // shared memory (padded rows: conflict-free), one warp per query (resp. key) row.
 // Addressing: element (b, i, h, d) of X lives at X + b*bs + i*rs + h*hd + d.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace {
@@ -244,6 +246,8 @@ extern void sc_count_launch(int n);
 bool sc_attn_mma_supported(const sc_attn_desc* a);
 int sc_attention_fwd_mma(const sc_attn_desc* a, cudaStream_t st);
 int sc_attention_bwd_mma(const sc_attn_bwd_desc* g, float* delta, cudaStream_t st);
+bool sc_attn_tc_supported(const sc_attn_desc* a);
+int sc_attention_bwd_tc(const sc_attn_bwd_desc* g, float* delta, cudaStream_t st);
 
 extern "C" int sc_attention_fwd(const sc_attn_desc* a, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
@@ -270,6 +274,10 @@ extern "C" int sc_attention_bwd(const sc_attn_bwd_desc* g, void* stream) {
   int rc = check_desc(a, "sc_attention_bwd");
   if (rc) return rc;
   SC_CHECK_ARG(g->d_o && g->d_q && g->d_k && g->d_v && a->lse, "sc_attention_bwd: null pointer");
+  {
+    static const int use_tc = [] { const char* e = getenv("SC_ATT_TC"); return e ? atoi(e) : 1; }();
+    if (use_tc && !a->force_generic && g->delta_ws && sc_attn_tc_supported(a)) return sc_attention_bwd_tc(g, g->delta_ws, st);
+  }
   if (!a->force_generic && g->delta_ws && sc_attn_mma_supported(a)) return sc_attention_bwd_mma(g, g->delta_ws, st);
   const size_t smem_q = sizeof(float) * ((size_t)2 * a->Lk * (a->hd + 1) + (size_t)ATT_WARPS * a->Lk + 2 * ATT_WARPS * 64);
   const size_t smem_kv = sizeof(float) * ((size_t)2 * a->Lq * (a->hd + 1) + 2 * (size_t)a->Lq +

@@ -1,0 +1,351 @@
+// tcgen05 / TMEM attention backward for self-attention with head dim 64 and L <= 256 (vision L=196/48, text L=77
+// causal): replaces the autograd backward of nn.MultiheadAttention's bmm/softmax/bmm
+// (modules/module_seg_vit.py:189, modules/module_clip_ttransformer.py:46).
+//
+// One CTA per (sample, head).  Q, K, V, dO of the head are TMA-loaded once into 128B-swizzled smem (256 rows each).
+// Work is done in the TRANSPOSED domain per (key tile kt, query tile qt) of 128 x 128, so every product is a plain UMMA
+// whose operands are either the TMA tiles or the two bf16 tiles written by the softmax warps:
+//   S^T  = K_kt Q_qt^T          (A K-major, B K-major,  N = 128)  -> TMEM cols [0,128)
+//   dP^T = V_kt dO_qt^T         (A K-major, B K-major,  N = 128)  -> TMEM cols [128,256)
+//   softmax warps: P^T = exp2(S^T c - lse_q), dS^T = P^T (dP^T - delta_q)  -> smem tiles (bf16, K-major, 128 x 128)
+//   dV_kt += P^T  dO_qt         (A K-major tile,  B = dO MN-major, N = 64) -> TMEM cols [256,320)
+//   dK_kt += dS^T Q_qt          (A K-major tile,  B = Q  MN-major, N = 64) -> TMEM cols [320,384)
+//   dQ_qt += dS   K_kt          (A = dS^T tile read MN-major, B = K MN-major, N = 64) -> TMEM cols [384,448) / [448,512)
+// TMEM is used completely (512 columns).  Warps 0-7: softmax + epilogues (lane quarter = warp % 4, column half = warp / 4);
+// warp 8: TMA + MMA issue (one thread).
+#include "gemm_tc_common.cuh"
+
+namespace {
+using namespace tc;
+
+constexpr int HD = 64;
+constexpr int TILE = 128;
+constexpr int ROWS = 256;                      // padded rows per operand
+constexpr int OPER_BYTES = ROWS * 128;         // 32 KB
+constexpr int PT_BYTES = TILE * TILE * 2;      // 32 KB (two 64-wide k-blocks of 16 KB)
+constexpr int SM_Q = 0, SM_K = OPER_BYTES, SM_V = 2 * OPER_BYTES, SM_DO = 3 * OPER_BYTES;
+constexpr int SM_PT = 4 * OPER_BYTES, SM_DST = SM_PT + PT_BYTES;
+constexpr int SM_LSE = SM_DST + PT_BYTES;      // float[256] lse*log2e, float[256] delta
+constexpr int SM_BAR = SM_LSE + 2 * ROWS * 4;
+constexpr int SMEM_TOTAL = SM_BAR + 128;
+constexpr int NSOFT = 16;                      // softmax / epilogue warps: 4 per TMEM lane quarter x 32 columns
+constexpr int TC_THREADS = (NSOFT + 1) * 32;
+constexpr float LOG2E_F = 1.4426950408889634f;
+
+constexpr uint32_t TM_ST = 0, TM_DPT = 128, TM_DV = 256, TM_DK = 320, TM_DQ = 384;
+
+// smem descriptor with explicit leading / stride byte offsets (SWIZZLE_128B)
+SC_DEVINL uint64_t desc_sw128(uint32_t addr, uint32_t lbo, uint32_t sbo) {
+  uint64_t d = 0;
+  d |= (uint64_t)((addr & 0x3FFFF) >> 4);
+  d |= (uint64_t)(lbo >> 4) << 16;
+  d |= (uint64_t)(sbo >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+__host__ __device__ constexpr uint32_t make_idesc(int n, bool a_mn, bool b_mn) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((a_mn ? 1u : 0u) << 15) | ((b_mn ? 1u : 0u) << 16) | ((uint32_t)(n >> 3) << 17) |
+         ((uint32_t)(128 >> 4) << 24);
+}
+SC_DEVINL float ex2f(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+SC_DEVINL uint32_t pack_bf16(float lo, float hi) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+  return *(uint32_t*)&v;
+}
+SC_DEVINL void sts128u(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+
+// delta[b,h,i] = sum_d dO[b,i,h,d] * O[b,i,h,d]
+__global__ void attn_delta_kernel(const bf16* __restrict__ o, const bf16* __restrict__ d_o, long bs, long rs, int B, int H, int L,
+                                  float* __restrict__ delta) {
+  const long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (long)B * L * H) return;
+  const int h = t % H;
+  const long row = t / H;
+  const int b = row / L, i = row % L;
+  const long off = (long)b * bs + (long)i * rs + h * HD;
+  float s = 0.f;
+#pragma unroll
+  for (int c = 0; c < HD / 8; ++c) {
+    const uint4 a = *(const uint4*)(o + off + c * 8), g = *(const uint4*)(d_o + off + c * 8);
+    const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, gw[4] = {g.x, g.y, g.z, g.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float2 x = __bfloat1622float2(*(const __nv_bfloat162*)&aw[k]), y = __bfloat1622float2(*(const __nv_bfloat162*)&gw[k]);
+      s = fmaf(x.x, y.x, fmaf(x.y, y.y, s));
+    }
+  }
+  delta[((long)b * H + h) * L + i] = s;
+}
+
+SC_DEVINL void tmem_ld16(uint32_t taddr, float* v) {
+  uint32_t* r = (uint32_t*)v;
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+SC_DEVINL void store16_bf16(bf16* dst, const float* v, float scale) {
+  uint4 u, w;
+  u.x = pack_bf16(v[0] * scale, v[1] * scale); u.y = pack_bf16(v[2] * scale, v[3] * scale);
+  u.z = pack_bf16(v[4] * scale, v[5] * scale); u.w = pack_bf16(v[6] * scale, v[7] * scale);
+  w.x = pack_bf16(v[8] * scale, v[9] * scale); w.y = pack_bf16(v[10] * scale, v[11] * scale);
+  w.z = pack_bf16(v[12] * scale, v[13] * scale); w.w = pack_bf16(v[14] * scale, v[15] * scale);
+  *(uint4*)dst = u;
+  *(uint4*)(dst + 8) = w;
+}
+
+template <bool CAUSAL>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                   const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmdO, sc_attn_bwd_desc gd,
+                   const float* __restrict__ delta) {
+  const sc_attn_desc& a = gd.fwd;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  if ((smem_u32(smem) & 1023u) != 0u) __trap();
+  const uint32_t sbase = smem_u32(smem);
+  uint64_t* bars = (uint64_t*)(smem + SM_BAR);
+  uint64_t* bar_load = bars;          // TMA bytes landed
+  uint64_t* bar_s = bars + 1;         // S / dP ready (commit)
+  uint64_t* bar_p = bars + 2;         // P / dS tiles written, S / dP consumed (all softmax warps)
+  uint64_t* bar_done = bars + 3;      // dV/dK/dQ MMAs of the pair retired (commit): tiles reusable
+  uint64_t* bar_dkv = bars + 4;       // dV/dK of a key tile final (commit)
+  uint64_t* bar_dkv_free = bars + 5;  // epilogue read dV/dK (all softmax warps)
+  uint32_t* tmem_slot = (uint32_t*)(bars + 8);
+  float* sLse = (float*)(smem + SM_LSE);
+  float* sDelta = sLse + ROWS;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int h = blockIdx.x, b = blockIdx.y;
+  const int L = a.Lq;
+  const int ntile = (L + TILE - 1) / TILE;
+
+  if (threadIdx.x == 0) {
+    mbar_init(bar_load, 1);
+    mbar_init(bar_s, 1);
+    mbar_init(bar_p, NSOFT);
+    mbar_init(bar_done, 1);
+    mbar_init(bar_dkv, 1);
+    mbar_init(bar_dkv_free, NSOFT);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  if (warp == NSOFT) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if (lane == 0) {
+      // TMA: the four operands of this (sample, head): rows b*L .. (+ntile*128), columns h*64 .. (+64)
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+  }
+  for (int i = threadIdx.x; i < ROWS; i += TC_THREADS) {
+    const long o = ((long)b * a.H + h) * L + i;
+    sLse[i] = i < L ? a.lse[o] * LOG2E_F : 0.f;
+    sDelta[i] = i < L ? delta[o] : 0.f;
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const float c = a.scale * LOG2E_F;
+
+  if (warp == NSOFT) {
+    if (lane == 0) {
+      const int box_bytes = ntile * TILE * 128;
+      mbar_expect_tx(bar_load, 4 * box_bytes);
+      tma_load_2d(&tmQ, bar_load, smem + SM_Q, h * HD, b * L);
+      tma_load_2d(&tmK, bar_load, smem + SM_K, h * HD, b * L);
+      tma_load_2d(&tmV, bar_load, smem + SM_V, h * HD, b * L);
+      tma_load_2d(&tmdO, bar_load, smem + SM_DO, h * HD, b * L);
+      mbar_wait(bar_load, 0);
+      tcgen05_fence_after();
+      constexpr uint32_t ID_S = make_idesc(128, false, false);   // S, dP : A K-major, B K-major
+      constexpr uint32_t ID_TT = make_idesc(64, true, true);     // dV, dK: A = tile read MN-major, B MN-major
+      constexpr uint32_t ID_NT = make_idesc(64, false, true);    // dQ    : A = tile K-major,       B MN-major
+      uint32_t ph_p = 0, ph_free = 0;
+      for (int kt = 0; kt < ntile; ++kt) {
+        const int q_first = CAUSAL ? kt : 0;       // query tiles entirely before the key tile see nothing
+        for (int qt = q_first; qt < ntile; ++qt) {
+          // S = Q_qt K_kt^T and dP = dO_qt V_kt^T (their TMEM columns were released by bar_p of the previous pair)
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk) {
+            const uint64_t dq_ = desc_sw128(sbase + SM_Q + qt * 16384 + kk * 32, 16, 1024);
+            const uint64_t dk_ = desc_sw128(sbase + SM_K + kt * 16384 + kk * 32, 16, 1024);
+            tcgen05_mma_f16(tmem + TM_ST, dq_, dk_, ID_S, kk > 0);
+          }
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk) {
+            const uint64_t do_ = desc_sw128(sbase + SM_DO + qt * 16384 + kk * 32, 16, 1024);
+            const uint64_t dv_ = desc_sw128(sbase + SM_V + kt * 16384 + kk * 32, 16, 1024);
+            tcgen05_mma_f16(tmem + TM_DPT, do_, dv_, ID_S, kk > 0);
+          }
+          tcgen05_commit(bar_s);
+          mbar_wait(bar_p, ph_p);
+          ph_p ^= 1;
+          tcgen05_fence_after();
+          if (qt == q_first && kt > 0) {             // dV/dK accumulators of the previous key tile must have been read
+            mbar_wait(bar_dkv_free, ph_free);
+            ph_free ^= 1;
+            tcgen05_fence_after();
+          }
+#pragma unroll
+          for (int kq = 0; kq < 8; ++kq) {           // contraction over the 128 queries of this tile (tile rows)
+            // tile [query rows][key cols] read as MN-major A: 64-key chunks 16 KB apart (LBO), 8-query groups 1 KB (SBO)
+            const uint64_t dpa = desc_sw128(sbase + SM_PT + kq * 2048, 16384, 1024);
+            const uint64_t dsa = desc_sw128(sbase + SM_DST + kq * 2048, 16384, 1024);
+            const uint64_t dob = desc_sw128(sbase + SM_DO + (qt * TILE + kq * 16) * 128, 8192, 1024);
+            const uint64_t dqb = desc_sw128(sbase + SM_Q + (qt * TILE + kq * 16) * 128, 8192, 1024);
+            tcgen05_mma_f16(tmem + TM_DV, dpa, dob, ID_TT, (qt > q_first || kq > 0));
+            tcgen05_mma_f16(tmem + TM_DK, dsa, dqb, ID_TT, (qt > q_first || kq > 0));
+          }
+#pragma unroll
+          for (int kk = 0; kk < 8; ++kk) {           // contraction over the 128 keys of this tile (tile columns)
+            const uint64_t dsa = desc_sw128(sbase + SM_DST + (kk >> 2) * 16384 + (kk & 3) * 32, 16, 1024);
+            const uint64_t dkb = desc_sw128(sbase + SM_K + (kt * TILE + kk * 16) * 128, 8192, 1024);
+            tcgen05_mma_f16(tmem + TM_DQ + qt * 64, dsa, dkb, ID_NT, (kt > 0 || kk > 0));
+          }
+          tcgen05_commit(bar_done);
+        }
+        tcgen05_commit(bar_dkv);
+      }
+    }
+  } else {
+    // ---------------- softmax + epilogue warps: TMEM lane quarter = warp % 4, 32-column group = warp / 4
+    const int quarter = warp & 3, cg = warp >> 2;
+    const uint32_t lane_off = (uint32_t)(quarter * 32) << 16;
+    const int r = quarter * 32 + lane;                  // row inside the tile
+    uint32_t ph_s = 0, ph_done = 0, ph_dkv = 0;
+    int pair = 0;
+    for (int kt = 0; kt < ntile; ++kt) {
+      const int q_first = CAUSAL ? kt : 0;
+      for (int qt = q_first; qt < ntile; ++qt, ++pair) {
+        const int qi = qt * TILE + r;                    // this thread's query
+        const int key0 = kt * TILE + cg * 32;            // first key of this warp's column group
+        const float lse2 = sLse[qi], dl = sDelta[qi];
+        mbar_wait(bar_s, ph_s);
+        ph_s ^= 1;
+        if (pair > 0) {                                  // the previous pair's MMAs must be done reading the tiles
+          mbar_wait(bar_done, ph_done);
+          ph_done ^= 1;
+        }
+        tcgen05_fence_after();
+        uint32_t pk[16], dk[16];                         // packed bf16 pairs of 32 columns
+        const bool warp_live = (qt * TILE + quarter * 32 < L) && key0 < L && (!CAUSAL || key0 <= qt * TILE + quarter * 32 + 31);
+        if (warp_live) {
+          float s[32], dp[32];
+          tmem_ld32(tmem + lane_off + TM_ST + cg * 32, s);
+          tmem_ld32(tmem + lane_off + TM_DPT + cg * 32, dp);
+#pragma unroll
+          for (int j = 0; j < 32; j += 2) {
+            const int k0 = key0 + j;
+            const bool ok0 = qi < L && k0 < L && (!CAUSAL || k0 <= qi);
+            const bool ok1 = qi < L && k0 + 1 < L && (!CAUSAL || k0 + 1 <= qi);
+            const float p0 = ok0 ? ex2f(fmaf(s[j], c, -lse2)) : 0.f;
+            const float p1 = ok1 ? ex2f(fmaf(s[j + 1], c, -lse2)) : 0.f;
+            const float d0 = ok0 ? p0 * (dp[j] - dl) : 0.f, d1 = ok1 ? p1 * (dp[j + 1] - dl) : 0.f;
+            pk[j / 2] = pack_bf16(p0, p1);
+            dk[j / 2] = pack_bf16(d0, d1);
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) pk[j] = dk[j] = 0u;
+        }
+        // K-major 128B-swizzled tile [query rows][key cols]: k-block cg/2, 16-byte chunks (cg&1)*4 + j
+        const uint32_t rowp = sbase + SM_PT + (cg >> 1) * 16384 + r * 128, rowd = sbase + SM_DST + (cg >> 1) * 16384 + r * 128;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const uint32_t off = (uint32_t)((((cg & 1) * 4 + j) ^ (r & 7)) << 4);
+          sts128u(rowp + off, pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+          sts128u(rowd + off, dk[4 * j], dk[4 * j + 1], dk[4 * j + 2], dk[4 * j + 3]);
+        }
+        tcgen05_fence_before();
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the MMA (async proxy)
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_p);
+      }
+      // ---- dV / dK of this key tile (TMEM lanes = keys); this warp handles 16 of the 64 head-dim columns
+      mbar_wait(bar_dkv, ph_dkv);
+      ph_dkv ^= 1;
+      tcgen05_fence_after();
+      {
+        float v[16], k[16];
+        tmem_ld16(tmem + lane_off + TM_DV + cg * 16, v);
+        tmem_ld16(tmem + lane_off + TM_DK + cg * 16, k);
+        tcgen05_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_dkv_free);
+        const int key = kt * TILE + r;
+        if (key < L) {
+          store16_bf16((bf16*)gd.d_v + (long)b * a.v_bs + (long)key * a.v_rs + h * HD + cg * 16, v, 1.0f);
+          store16_bf16((bf16*)gd.d_k + (long)b * a.k_bs + (long)key * a.k_rs + h * HD + cg * 16, k, a.scale);
+        }
+      }
+    }
+    // ---- dQ (TMEM lanes = queries); the last bar_done covers every MMA
+    mbar_wait(bar_done, ph_done);
+    tcgen05_fence_after();
+    for (int qt = 0; qt < ntile; ++qt) {
+      float v[16];
+      tmem_ld16(tmem + lane_off + TM_DQ + qt * 64 + cg * 16, v);
+      const int qi = qt * TILE + r;
+      if (qi < L) store16_bf16((bf16*)gd.d_q + (long)b * a.q_bs + (long)qi * a.q_rs + h * HD + cg * 16, v, a.scale);
+    }
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == NSOFT) {
+    tcgen05_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
+  }
+}
+
+}  // namespace
+
+extern void sc_count_launch(int n);
+
+bool sc_attn_tc_supported(const sc_attn_desc* a) {
+  auto packed = [&](const void* p, long bs, long rs, int L) {
+    return ((uintptr_t)p & 15) == 0 && rs % 8 == 0 && bs == (long)L * rs;
+  };
+  return a->dtype == SC_BF16 && a->hd == 64 && a->Lq == a->Lk && a->Lq >= 16 && a->Lq <= 256 && a->B <= 65535 &&
+         packed(a->q, a->q_bs, a->q_rs, a->Lq) && packed(a->k, a->k_bs, a->k_rs, a->Lk) &&
+         packed(a->v, a->v_bs, a->v_rs, a->Lk) && packed(a->o, a->o_bs, a->o_rs, a->Lq);
+}
+
+int sc_attention_bwd_tc(const sc_attn_bwd_desc* g, float* delta, cudaStream_t st) {
+  const sc_attn_desc* a = &g->fwd;
+  const int L = a->Lq, ntile = (L + TILE - 1) / TILE;
+  const long rows = (long)a->B * L;
+  CUtensorMap tq, tk, tv, tdo;
+  int rc;
+  // 2-D maps over the [B*L, H*64] column slices; box = 64 columns x ntile*128 rows, zero fill past the last row
+  if ((rc = sc_get_tensor_map(a->q, (uint64_t)a->H * HD, rows, a->q_rs, 64, ntile * TILE, &tq))) return rc;
+  if ((rc = sc_get_tensor_map(a->k, (uint64_t)a->H * HD, rows, a->k_rs, 64, ntile * TILE, &tk))) return rc;
+  if ((rc = sc_get_tensor_map(a->v, (uint64_t)a->H * HD, rows, a->v_rs, 64, ntile * TILE, &tv))) return rc;
+  if ((rc = sc_get_tensor_map(g->d_o, (uint64_t)a->H * HD, rows, a->o_rs, 64, ntile * TILE, &tdo))) return rc;
+  sc_count_launch(2);
+  const long n = rows * a->H;
+  attn_delta_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>((const bf16*)a->o, (const bf16*)g->d_o, a->o_bs, a->o_rs, a->B,
+                                                                 a->H, L, delta);
+  dim3 grid(a->H, a->B);
+  if (a->causal) {
+    static bool cfg = false;
+    if (!cfg) { SC_CUDA(cudaFuncSetAttribute(attn_bwd_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL)); cfg = true; }
+    attn_bwd_tc_kernel<true><<<grid, TC_THREADS, SMEM_TOTAL, st>>>(tq, tk, tv, tdo, *g, delta);
+  } else {
+    static bool cfg = false;
+    if (!cfg) { SC_CUDA(cudaFuncSetAttribute(attn_bwd_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL)); cfg = true; }
+    attn_bwd_tc_kernel<false><<<grid, TC_THREADS, SMEM_TOTAL, st>>>(tq, tk, tv, tdo, *g, delta);
+  }
+  SC_LAUNCH_CHECK();
+  return SC_OK;
+}

@@ -115,6 +115,11 @@ int sc_select_epilogue(const sc_gemm_desc* d, int splits) {
     } else if (aux && d->mul_aux_dtype == SC_BF16 && d->mul_aux_act == SC_ACT_QUICKGELU && !bias && !resid && !c2 &&
                d->act == SC_ACT_NONE && out_bf16) {
       ef = EF_MULAUX_QGELU;
+    } else if (bias && c2 && d->c2_dtype == SC_BF16 && out_bf16 && d->act == SC_ACT_GELU_ERF && !resid && !aux) {
+      ef = EF_BIAS | EF_GELU | EF_C2;
+    } else if (aux && d->mul_aux_dtype == SC_BF16 && d->mul_aux_act == SC_ACT_GELU_ERF && !bias && !resid && !c2 &&
+               d->act == SC_ACT_NONE && out_bf16) {
+      ef = EF_MULAUX_GELU;
     }
   }
   return ef;
@@ -283,7 +288,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             if constexpr (EF != EF_GENERIC && (EF & EF_RESID) != 0) {
               if (m < ep.M) pre[i] = *(const float4*)(ep.residual + (long)m * ep.ldr + n);
             }
-            if constexpr (EF != EF_GENERIC && (EF & EF_MULAUX_QGELU) != 0) {
+            if constexpr (EF != EF_GENERIC && (EF & (EF_MULAUX_QGELU | EF_MULAUX_GELU)) != 0) {
               if (m < ep.M) {
                 const uint2 u = *(const uint2*)((const bf16*)ep.mul_aux + (long)m * ep.ldc + n);
                 pre[i].x = __uint_as_float(u.x);
@@ -409,11 +414,13 @@ int sc_gemm_tc(const sc_gemm_desc* d, cudaStream_t st) {
     if (ef == 0) SC_L(BN_, false, false, 0)                                                  \
     if (ef == (EF_BIAS | EF_QGELU | EF_C2)) SC_L(BN_, false, false, EF_BIAS | EF_QGELU | EF_C2) \
     if (ef == (EF_BIAS | EF_RESID | EF_OUT_F32)) SC_L(BN_, false, false, EF_BIAS | EF_RESID | EF_OUT_F32) \
+    if (ef == (EF_BIAS | EF_GELU | EF_C2)) SC_L(BN_, false, false, EF_BIAS | EF_GELU | EF_C2)  \
     SC_L(BN_, false, false, EF_GENERIC)                                                      \
   }                                                                                          \
   if (!a_mn && b_mn) {                                                                       \
     if (ef == 0) SC_L(BN_, false, true, 0)                                                   \
     if (ef == EF_MULAUX_QGELU) SC_L(BN_, false, true, EF_MULAUX_QGELU)                       \
+    if (ef == EF_MULAUX_GELU) SC_L(BN_, false, true, EF_MULAUX_GELU)                         \
     SC_L(BN_, false, true, EF_GENERIC)                                                       \
   }                                                                                          \
   if (a_mn && b_mn) {                                                                        \

@@ -197,7 +197,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             if constexpr (EF != EF_GENERIC && (EF & EF_RESID) != 0) {
               if (m < ep.M) pre[i] = *(const float4*)(ep.residual + (long)m * ep.ldr + n);
             }
-            if constexpr (EF != EF_GENERIC && (EF & EF_MULAUX_QGELU) != 0) {
+            if constexpr (EF != EF_GENERIC && (EF & (EF_MULAUX_QGELU | EF_MULAUX_GELU)) != 0) {
               if (m < ep.M) {
                 const uint2 u = *(const uint2*)((const bf16*)ep.mul_aux + (long)m * ep.ldc + n);
                 pre[i].x = __uint_as_float(u.x);
@@ -300,11 +300,13 @@ int sc_gemm_tc2(const sc_gemm_desc* d, cudaStream_t st) {
     if (ef == 0) SC_L2(false, false, 0)
     if (ef == (EF_BIAS | EF_QGELU | EF_C2)) SC_L2(false, false, EF_BIAS | EF_QGELU | EF_C2)
     if (ef == (EF_BIAS | EF_RESID | EF_OUT_F32)) SC_L2(false, false, EF_BIAS | EF_RESID | EF_OUT_F32)
+    if (ef == (EF_BIAS | EF_GELU | EF_C2)) SC_L2(false, false, EF_BIAS | EF_GELU | EF_C2)
     SC_L2(false, false, EF_GENERIC)
   }
   if (!a_mn && b_mn) {
     if (ef == 0) SC_L2(false, true, 0)
     if (ef == EF_MULAUX_QGELU) SC_L2(false, true, EF_MULAUX_QGELU)
+    if (ef == EF_MULAUX_GELU) SC_L2(false, true, EF_MULAUX_GELU)
     SC_L2(false, true, EF_GENERIC)
   }
   if (ef == (EF_ATOMIC | EF_OUT_F32)) SC_L2(true, true, EF_ATOMIC | EF_OUT_F32)

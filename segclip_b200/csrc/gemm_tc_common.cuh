@@ -92,6 +92,8 @@ enum : int {
   EF_OUT_F32 = 16,      // fp32 output (default bf16)
   EF_MULAUX_QGELU = 32, // * QuickGELU'(aux) (fused activation backward, aux bf16)
   EF_ATOMIC = 64,       // split-K: atomic accumulate into fp32 C
+  EF_GELU = 128,        // exact erf GELU (MAE decoder / proj_o MLP)
+  EF_MULAUX_GELU = 256, // * GELU'(aux)
   EF_GENERIC = 1 << 20
 };
 
@@ -131,17 +133,28 @@ SC_DEVINL void epi4_fast(const EpiParams& p, int m, int n, float4 v, const float
     if constexpr ((F & EF_BIAS) != 0) { v.x += b4.x; v.y += b4.y; v.z += b4.z; v.w += b4.w; }
     if constexpr ((F & EF_C2) != 0) *(uint2*)((bf16*)p.C2 + off) = pack4_bf16(v);
     if constexpr ((F & EF_QGELU) != 0) { v.x = qgelu_fast(v.x); v.y = qgelu_fast(v.y); v.z = qgelu_fast(v.z); v.w = qgelu_fast(v.w); }
+    if constexpr ((F & EF_GELU) != 0) {
+      v.x = act_fwd(v.x, SC_ACT_GELU_ERF); v.y = act_fwd(v.y, SC_ACT_GELU_ERF);
+      v.z = act_fwd(v.z, SC_ACT_GELU_ERF); v.w = act_fwd(v.w, SC_ACT_GELU_ERF);
+    }
     if constexpr ((F & EF_MULAUX_QGELU) != 0) {
       const uint32_t ux = __float_as_uint(pre.x), uy = __float_as_uint(pre.y);   // prefetched bf16x4
       const float2 a = __bfloat1622float2(*(const __nv_bfloat162*)&ux), b = __bfloat1622float2(*(const __nv_bfloat162*)&uy);
       v.x *= qgelu_grad_fast(a.x); v.y *= qgelu_grad_fast(a.y); v.z *= qgelu_grad_fast(b.x); v.w *= qgelu_grad_fast(b.y);
     }
+    if constexpr ((F & EF_MULAUX_GELU) != 0) {
+      const uint32_t ux = __float_as_uint(pre.x), uy = __float_as_uint(pre.y);
+      const float2 a = __bfloat1622float2(*(const __nv_bfloat162*)&ux), b = __bfloat1622float2(*(const __nv_bfloat162*)&uy);
+      v.x *= act_grad(a.x, SC_ACT_GELU_ERF); v.y *= act_grad(a.y, SC_ACT_GELU_ERF);
+      v.z *= act_grad(b.x, SC_ACT_GELU_ERF); v.w *= act_grad(b.y, SC_ACT_GELU_ERF);
+    }
     if constexpr ((F & EF_RESID) != 0) {
       v.x += pre.x; v.y += pre.y; v.z += pre.z; v.w += pre.w;    // prefetched residual
     }
     if constexpr ((F & EF_ATOMIC) != 0) {
-      float* c = (float*)p.C + off;
-      atomicAdd(c, v.x); atomicAdd(c + 1, v.y); atomicAdd(c + 2, v.z); atomicAdd(c + 3, v.w);
+      // one 16-byte vector reduction instead of four scalar atomics (split-K wgrad: fp32 accumulate in L2)
+      asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"((float*)p.C + off), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
+                   : "memory");
     } else if constexpr ((F & EF_OUT_F32) != 0) {
       *(float4*)((float*)p.C + off) = v;
     } else {

@@ -75,34 +75,53 @@ __global__ void __launch_bounds__(256) ln_fwd_kernel(sc_ln_desc d) {
   }
 }
 
+// Backward: one warp per row (grid-stride).  Each warp keeps its dgamma / dbeta partial sums in a PRIVATE slice of
+// shared memory (plain vector load-add-store, no atomics, no conflicts) instead of 2*NV*4 registers per thread: the
+// kernel stays under ~80 registers so three CTAs (24 warps) are resident per SM and enough reads are in flight for HBM.
 template <typename TDY, typename TX, typename TDX, int NV>
-__global__ void __launch_bounds__(256) ln_bwd_kernel(sc_ln_bwd_desc d) {
-  __shared__ float red[8][32 * 4 + 1];
+__global__ void __launch_bounds__(256, 3) ln_bwd_kernel(sc_ln_bwd_desc d) {
+  extern __shared__ __align__(16) float sacc[];          // [8 warps][2][D]
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int D4 = d.D >> 2;
-  float4 dg[NV], db[NV];
-#pragma unroll
-  for (int j = 0; j < NV; ++j) dg[j] = db[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-
+  const bool want_param = d.dgamma != nullptr;
+  float* mine = sacc + (size_t)warp * 2 * d.D;
+  if (want_param) {
+    for (int i = lane; i < 2 * d.D; i += 32) mine[i] = 0.f;
+    __syncwarp();
+  }
+  const bool acc = d.dx && d.accumulate_dx;
   for (long row = (long)blockIdx.x * 8 + warp; row < d.rows; row += (long)gridDim.x * 8) {
     const TX* x = (const TX*)d.x + row * d.D;
     const TDY* dy = (const TDY*)d.dy + remap_row(row, d.in_group, d.out_group, d.out_off) * d.D;
+    float4 xv[NV], dv[NV], old[NV];
+#pragma unroll
+    for (int j = 0; j < NV; ++j) {      // every global read of the row is issued up front
+      const int i4 = lane + 32 * j;
+      const bool in = i4 < D4;
+      xv[j] = in ? load4<TX>(x, i4) : make_float4(0.f, 0.f, 0.f, 0.f);
+      dv[j] = in ? load4<TDY>(dy, i4) : make_float4(0.f, 0.f, 0.f, 0.f);
+      old[j] = (acc && in) ? load4<TDX>((const TDX*)d.dx + row * d.D, i4) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
     const float mean = d.mean[row], rstd = d.rstd[row];
-    float4 xh[NV], g[NV];
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
     for (int j = 0; j < NV; ++j) {
-      int i4 = lane + 32 * j;
+      const int i4 = lane + 32 * j;
       if (i4 < D4) {
-        float4 xv = load4<TX>(x, i4), dv = load4<TDY>(dy, i4), gm = *(const float4*)(d.gamma + i4 * 4);
-        xh[j] = make_float4((xv.x - mean) * rstd, (xv.y - mean) * rstd, (xv.z - mean) * rstd, (xv.w - mean) * rstd);
-        g[j] = make_float4(dv.x * gm.x, dv.y * gm.y, dv.z * gm.z, dv.w * gm.w);
-        s1 += g[j].x + g[j].y + g[j].z + g[j].w;
-        s2 += g[j].x * xh[j].x + g[j].y * xh[j].y + g[j].z * xh[j].z + g[j].w * xh[j].w;
-        dg[j].x += dv.x * xh[j].x; dg[j].y += dv.y * xh[j].y; dg[j].z += dv.z * xh[j].z; dg[j].w += dv.w * xh[j].w;
-        db[j].x += dv.x; db[j].y += dv.y; db[j].z += dv.z; db[j].w += dv.w;
-      } else {
-        xh[j] = g[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+        const float4 gm = __ldg((const float4*)(d.gamma + i4 * 4));
+        xv[j] = make_float4((xv[j].x - mean) * rstd, (xv[j].y - mean) * rstd, (xv[j].z - mean) * rstd, (xv[j].w - mean) * rstd);
+        const float gx = dv[j].x * gm.x, gy = dv[j].y * gm.y, gz = dv[j].z * gm.z, gw = dv[j].w * gm.w;
+        s1 += gx + gy + gz + gw;
+        s2 += gx * xv[j].x + gy * xv[j].y + gz * xv[j].z + gw * xv[j].w;
+        if (want_param) {
+          float4* sg = (float4*)(mine + i4 * 4);
+          float4* sb = (float4*)(mine + d.D + i4 * 4);
+          float4 a = *sg, b = *sb;
+          a.x += dv[j].x * xv[j].x; a.y += dv[j].y * xv[j].y; a.z += dv[j].z * xv[j].z; a.w += dv[j].w * xv[j].w;
+          b.x += dv[j].x; b.y += dv[j].y; b.z += dv[j].z; b.w += dv[j].w;
+          *sg = a;
+          *sb = b;
+        }
       }
     }
     const float c1 = warp_sum(s1) / d.D, c2 = warp_sum(s2) / d.D;
@@ -110,44 +129,27 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(sc_ln_bwd_desc d) {
       TDX* dx = (TDX*)d.dx + row * d.D;
 #pragma unroll
       for (int j = 0; j < NV; ++j) {
-        int i4 = lane + 32 * j;
+        const int i4 = lane + 32 * j;
         if (i4 < D4) {
+          const float4 gm = __ldg((const float4*)(d.gamma + i4 * 4));
           float4 o;
-          o.x = rstd * (g[j].x - c1 - xh[j].x * c2);
-          o.y = rstd * (g[j].y - c1 - xh[j].y * c2);
-          o.z = rstd * (g[j].z - c1 - xh[j].z * c2);
-          o.w = rstd * (g[j].w - c1 - xh[j].w * c2);
-          if (d.accumulate_dx) {
-            float4 p = load4<TDX>(dx, i4);
-            o.x += p.x; o.y += p.y; o.z += p.z; o.w += p.w;
-          }
+          o.x = rstd * (dv[j].x * gm.x - c1 - xv[j].x * c2) + old[j].x;
+          o.y = rstd * (dv[j].y * gm.y - c1 - xv[j].y * c2) + old[j].y;
+          o.z = rstd * (dv[j].z * gm.z - c1 - xv[j].z * c2) + old[j].z;
+          o.w = rstd * (dv[j].w * gm.w - c1 - xv[j].w * c2) + old[j].w;
           store4<TDX>(dx, i4, o);
           if (d.dx_copy_bf16) store4<bf16>((bf16*)d.dx_copy_bf16 + row * d.D, i4, o);
         }
       }
     }
   }
-  if (!d.dgamma) return;  // uniform across the block
-  // reduce the 8 warps' partial dgamma/dbeta through smem, then one atomic per column per block
+  if (!want_param) return;
+  __syncthreads();
+  for (int i = threadIdx.x; i < 2 * d.D; i += 256) {
+    float s = 0.f;
 #pragma unroll
-  for (int pass = 0; pass < 2; ++pass) {
-#pragma unroll
-    for (int j = 0; j < NV; ++j) {
-      __syncthreads();
-      float4 v = pass == 0 ? dg[j] : db[j];
-      red[warp][lane * 4 + 0] = v.x;
-      red[warp][lane * 4 + 1] = v.y;
-      red[warp][lane * 4 + 2] = v.z;
-      red[warp][lane * 4 + 3] = v.w;
-      __syncthreads();
-      if (threadIdx.x < 128) {
-        float s = 0.f;
-#pragma unroll
-        for (int w = 0; w < 8; ++w) s += red[w][threadIdx.x];
-        int col = (threadIdx.x >> 2) * 4 + 128 * j + (threadIdx.x & 3);
-        if (col < d.D) atomicAdd((pass == 0 ? d.dgamma : d.dbeta) + col, s);
-      }
-    }
+    for (int w = 0; w < 8; ++w) s += sacc[(size_t)w * 2 * d.D + i];
+    atomicAdd((i < d.D ? d.dgamma : d.dbeta - d.D) + i, s);
   }
 }
 
@@ -174,8 +176,14 @@ template <typename TDY, typename TX, typename TDX>
 int launch_bwd(const sc_ln_bwd_desc& d, cudaStream_t st) {
   const int nv = ceil_div(d.D, 128);
   long g = ceil_div(d.rows, 8);
-  const int grid = (int)(g < 4L * sc_num_sms() ? g : 4L * sc_num_sms());
-#define SC_LN_CASE(NV_) ln_bwd_kernel<TDY, TX, TDX, NV_><<<grid, 256, 0, st>>>(d)
+  const int grid = (int)(g < 3L * sc_num_sms() ? g : 3L * sc_num_sms());      // three resident CTAs per SM
+  const size_t smem = d.dgamma ? (size_t)8 * 2 * d.D * sizeof(float) : 0;
+#define SC_LN_CASE(NV_)                                                                                      \
+  {                                                                                                          \
+    static bool cfg = false;                                                                                 \
+    if (!cfg) { cudaFuncSetAttribute(ln_bwd_kernel<TDY, TX, TDX, NV_>, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536); cfg = true; } \
+    ln_bwd_kernel<TDY, TX, TDX, NV_><<<grid, 256, smem, st>>>(d);                                           \
+  }
   switch (nv) {
     case 1: SC_LN_CASE(1); break;
     case 2: SC_LN_CASE(2); break;
