@@ -274,46 +274,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll 1
       for (int c = 0; c < BN / 2 / 32; ++c) {
         float v[32];
-        // issue the global reads of this chunk (bias, residual / activation-gradient operand) first: their DRAM latency
-        // overlaps the TMEM load and the smem transpose instead of serialising per row
-        const int n = nbase + c * 32 + l7 * 4;
-        float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
-        float4 pre[8];
-        if (n < ep.N) {
-          if constexpr (EF != EF_GENERIC && (EF & EF_BIAS) != 0) b4 = __ldg((const float4*)(ep.bias + n));
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const int m = mrow0 + 4 * i + l3;
-            pre[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if constexpr (EF != EF_GENERIC && (EF & EF_RESID) != 0) {
-              if (m < ep.M) pre[i] = *(const float4*)(ep.residual + (long)m * ep.ldr + n);
-            }
-            if constexpr (EF != EF_GENERIC && (EF & (EF_MULAUX_QGELU | EF_MULAUX_GELU)) != 0) {
-              if (m < ep.M) {
-                const uint2 u = *(const uint2*)((const bf16*)ep.mul_aux + (long)m * ep.ldc + n);
-                pre[i].x = __uint_as_float(u.x);
-                pre[i].y = __uint_as_float(u.y);
-              }
-            }
-          }
-        }
+        float4 b4, pre[8];
+        const int n0 = nbase + c * 32;
+        epi_prefetch<EF>(ep, lane, mrow0, n0, b4, pre);     // global reads first: latency overlaps the TMEM load
         tmem_ld32(taddr + c * 32, v);
-        // transpose through the warp's private smem patch (32 rows x 128 B, 16-byte chunks XOR-swizzled by row)
-        // so that global loads/stores of the epilogue are full-line: 8 lanes cover 32 consecutive columns of a row.
-        __syncwarp();
-#pragma unroll
-        for (int j = 0; j < 8; ++j)
-          sts128(stage + lane * 128 + ((j ^ l7) << 4), v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-        __syncwarp();
-        if (n < ep.N) {
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const int r = 4 * i + l3;
-            const float4 x = lds128(stage + r * 128 + ((l7 ^ (r & 7)) << 4));
-            const int m = mrow0 + r;
-            if (m < ep.M) epi4_fast<EF>(ep, m, n, x, b4, pre[i]);
-          }
-        }
+        epi_finish<EF>(ep, v, stage, lane, mrow0, n0, b4, pre);
       }
       tcgen05_fence_before();
       __syncwarp();

@@ -163,6 +163,146 @@ SC_DEVINL void epi4_fast(const EpiParams& p, int m, int n, float4 v, const float
   }
 }
 
+SC_DEVINL void sts128b(uint32_t addr, const uint4& u) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(u.x), "r"(u.y), "r"(u.z), "r"(u.w) : "memory");
+}
+SC_DEVINL uint4 lds128b(uint32_t addr) {
+  uint4 u;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(u.x), "=r"(u.y), "=r"(u.z), "=r"(u.w) : "r"(addr) : "memory");
+  return u;
+}
+SC_DEVINL uint32_t pack2_bf16(float lo, float hi) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+  return *(uint32_t*)&v;
+}
+SC_DEVINL float2 unpack2_bf16(uint32_t u) { return __bfloat1622float2(*(const __nv_bfloat162*)&u); }
+
+// ---- per-chunk epilogue driver (one warp, 32 rows x 32 accumulator columns) --------------------------------------
+// bf16-output kinds do all column-wise math in the row-per-thread domain, pack to bf16 and transpose only 64 B per row
+// through the warp's smem patch (half the shared-memory traffic of an fp32 transpose: with K = 768 the UMMA operand
+// fetch already uses ~70 % of the SM's 128 B/clk shared-memory bandwidth, so the epilogue's share decides the speed).
+// fp32-output kinds (residual add, split-K accumulate, generic) transpose fp32.
+template <int EF>
+struct EpiKind {
+  static constexpr bool bf16_path = (EF != EF_GENERIC) && (EF & (EF_OUT_F32 | EF_ATOMIC | EF_RESID)) == 0;
+  static constexpr bool aux = (EF != EF_GENERIC) && (EF & (EF_MULAUX_QGELU | EF_MULAUX_GELU)) != 0;
+};
+
+template <int EF>
+SC_DEVINL void epi_prefetch(const EpiParams& ep, int lane, int mrow0, int n0, float4& b4, float4 (&pre)[8]) {
+  if constexpr (EpiKind<EF>::bf16_path) {
+    if constexpr (EpiKind<EF>::aux) {
+      const int c = lane & 3, n = n0 + c * 8;
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        const int m = mrow0 + 8 * t + (lane >> 2);
+        uint4 u = make_uint4(0u, 0u, 0u, 0u);
+        if (m < ep.M && n < ep.N) u = *(const uint4*)((const bf16*)ep.mul_aux + (long)m * ep.ldc + n);
+        pre[t] = make_float4(__uint_as_float(u.x), __uint_as_float(u.y), __uint_as_float(u.z), __uint_as_float(u.w));
+      }
+    }
+  } else {
+    const int l7 = lane & 7, l3 = lane >> 3;
+    const int n = n0 + l7 * 4;
+    b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (n < ep.N) {
+      if constexpr (EF != EF_GENERIC && (EF & EF_BIAS) != 0) b4 = __ldg((const float4*)(ep.bias + n));
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int m = mrow0 + 4 * i + l3;
+        pre[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if constexpr (EF != EF_GENERIC && (EF & EF_RESID) != 0) {
+          if (m < ep.M) pre[i] = *(const float4*)(ep.residual + (long)m * ep.ldr + n);
+        }
+      }
+    }
+  }
+}
+
+template <int EF>
+SC_DEVINL void epi_finish(const EpiParams& ep, float (&v)[32], uint32_t stage, int lane, int mrow0, int n0, const float4& b4,
+                          const float4 (&pre)[8]) {
+  if constexpr (EpiKind<EF>::bf16_path) {
+    // ---- row-per-thread math
+    if constexpr ((EF & EF_BIAS) != 0) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        if (n0 + 4 * j < ep.N) {                       // warp-uniform
+          const float4 b = __ldg((const float4*)(ep.bias + n0 + 4 * j));
+          v[4 * j] += b.x; v[4 * j + 1] += b.y; v[4 * j + 2] += b.z; v[4 * j + 3] += b.w;
+        }
+      }
+    }
+    const uint32_t rowaddr = stage + lane * 64;
+    const int sw = (lane >> 1) & 3;
+    __syncwarp();
+    if constexpr ((EF & EF_C2) != 0) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        sts128b(rowaddr + ((j ^ sw) << 4), make_uint4(pack2_bf16(v[8 * j], v[8 * j + 1]), pack2_bf16(v[8 * j + 2], v[8 * j + 3]),
+                                                       pack2_bf16(v[8 * j + 4], v[8 * j + 5]), pack2_bf16(v[8 * j + 6], v[8 * j + 7])));
+    }
+    if constexpr ((EF & EF_QGELU) != 0) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = qgelu_fast(v[j]);
+    }
+    if constexpr ((EF & EF_GELU) != 0) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = act_fwd(v[j], SC_ACT_GELU_ERF);
+    }
+    constexpr uint32_t out_tile = (EF & EF_C2) != 0 ? 2048u : 0u;
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      sts128b(rowaddr + out_tile + ((j ^ sw) << 4), make_uint4(pack2_bf16(v[8 * j], v[8 * j + 1]), pack2_bf16(v[8 * j + 2], v[8 * j + 3]),
+                                                                 pack2_bf16(v[8 * j + 4], v[8 * j + 5]), pack2_bf16(v[8 * j + 6], v[8 * j + 7])));
+    __syncwarp();
+    // ---- transposed, coalesced stores: 4 lanes x 16 B cover the 64 B of one row, 8 rows per instruction
+    const int c = lane & 3, n = n0 + c * 8;
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      const int row = 8 * t + (lane >> 2);
+      const int m = mrow0 + row;
+      const uint32_t a = stage + row * 64 + ((c ^ ((row >> 1) & 3)) << 4);
+      if (m < ep.M && n < ep.N) {
+        const long off = (long)m * ep.ldc + n;
+        if constexpr ((EF & EF_C2) != 0) *(uint4*)((bf16*)ep.C2 + off) = lds128b(a);
+        uint4 u = lds128b(a + out_tile);
+        if constexpr (EpiKind<EF>::aux) {
+          const uint32_t aw[4] = {__float_as_uint(pre[t].x), __float_as_uint(pre[t].y), __float_as_uint(pre[t].z), __float_as_uint(pre[t].w)};
+          uint32_t uw[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const float2 x = unpack2_bf16(uw[k]), g = unpack2_bf16(aw[k]);
+            float g0, g1;
+            if constexpr ((EF & EF_MULAUX_QGELU) != 0) { g0 = qgelu_grad_fast(g.x); g1 = qgelu_grad_fast(g.y); }
+            else { g0 = act_grad(g.x, SC_ACT_GELU_ERF); g1 = act_grad(g.y, SC_ACT_GELU_ERF); }
+            uw[k] = pack2_bf16(x.x * g0, x.y * g1);
+          }
+          u = make_uint4(uw[0], uw[1], uw[2], uw[3]);
+        }
+        *(uint4*)((bf16*)ep.C + off) = u;
+      }
+    }
+  } else {
+    const int l7 = lane & 7, l3 = lane >> 3;
+    __syncwarp();
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      sts128(stage + lane * 128 + ((j ^ l7) << 4), v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+    __syncwarp();
+    const int n = n0 + l7 * 4;
+    if (n < ep.N) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int r = 4 * i + l3;
+        const float4 x = lds128(stage + r * 128 + ((l7 ^ (r & 7)) << 4));
+        const int m = mrow0 + r;
+        if (m < ep.M) epi4_fast<EF>(ep, m, n, x, b4, pre[i]);
+      }
+    }
+  }
+}
+
 // Shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout), SWIZZLE_128B.
 //   K-major : rows of 128 B, 8-row swizzle atoms 1024 B apart (SBO); LBO unused (1).
 //   MN-major: 64-element (128 B) MN chunks; k rows 128 B apart, 8-k-row atoms SBO=1024 B apart,
