@@ -471,6 +471,7 @@ class Engine:
         pl.b(grp)
 
         # =============================================================== vision tower, main pass
+        pl.f("wait_image")        # the image H2D copy runs on a side stream underneath the text tower
         xv = vision_stem("v.stem", self.Lp, None)
         Mv = B * self.Lp
         dxv = buf("v.dx", (Mv, D), zero=True)          # gradient of the layers0 stream (many contributors)
@@ -659,7 +660,23 @@ class Engine:
         pl = self.plan(B)
         b = pl.bufs
         b["in.ids"].copy_(inputs["ids"], non_blocking=True)
-        b["in.image"].copy_(inputs["image"], non_blocking=True)
+        img = inputs["image"]
+        self._img_event = None
+        if img.device.type == "cpu":
+            # host image (the reference's data contract): copy on a side stream so it overlaps the text tower; the
+            # vision stem waits on the event ("wait_image" marker in the forward tape)
+            if getattr(self, "_copy_stream", None) is None:
+                self._copy_stream = torch.cuda.Stream(device=self.dev)
+            cur = torch.cuda.current_stream(self.dev)
+            self._copy_stream.wait_stream(cur)           # previous step's readers of in.image are done
+            with torch.cuda.stream(self._copy_stream):
+                if img.dtype == torch.float32 and img.dim() == 5:
+                    b["in.image"].copy_(img[:, 0], non_blocking=True)
+                else:
+                    b["in.image"].copy_(img.reshape(b["in.image"].shape).to(torch.float32), non_blocking=True)
+                self._img_event = self._copy_stream.record_event()
+        else:
+            b["in.image"].copy_(img.reshape(b["in.image"].shape), non_blocking=True)
         if inputs.get("seg") is not None:
             b["in.seg"].copy_(inputs["seg"].reshape(B, -1), non_blocking=True)
         b["in.u1"].copy_(noise["u1"], non_blocking=True)
@@ -683,6 +700,9 @@ class Engine:
                 if op == "force_pool":
                     if use_forced and forced.get("pool") is not None:
                         b["v.parg"].copy_(forced["pool"].to(torch.int32))
+                elif op == "wait_image":
+                    if self._img_event is not None:
+                        torch.cuda.current_stream(self.dev).wait_event(self._img_event)
                 else:
                     self._collective(op, pl)
             elif isinstance(op, tuple):

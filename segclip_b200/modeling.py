@@ -352,7 +352,10 @@ class SegCLIP(nn.Module):
         ids = ids.view(-1, ids.shape[-1]).to(dev, non_blocking=True)
         img = torch.as_tensor(image)
         b, pair, ch, h, w = img.shape
-        img = img[:, 0].to(dev, non_blocking=True).float()
+        if img.device.type != "cpu":
+            img = img[:, 0].float()                # device input: cast in place of the reference's .float() (modeling.py:182)
+        elif img.dtype != torch.float32:
+            img = img[:, 0].float()                # float64 host arrays of the reference loaders: cast once on the host
         seg = None
         if self.use_seglabel:
             seg = torch.as_tensor(image_seg)[:, 0].to(dev, non_blocking=True).reshape(b, -1).long()
