@@ -93,6 +93,8 @@ typedef struct {
   const void* mul_aux;   /* optional [M,N] (leading dim ldc): v *= act'(mul_aux) after act -- fused QuickGELU/GELU backward */
   int32_t mul_aux_dtype;
   int32_t mul_aux_act;
+  float* colsum_out;     /* optional fp32 [N]: colsum_out[n] += sum_m C[m,n] (bias gradient fused into the dgrad that produces dY);
+                            only with bf16 C on the tensor-core path */
 } sc_gemm_desc;
 
 int sc_gemm(const sc_gemm_desc* d, void* stream);
@@ -140,6 +142,8 @@ typedef struct {
   float* dgamma;
   float* dbeta;
   int32_t in_group, out_group, out_off;
+  float* dx_colsum; /* optional fp32 [D]: += column sums of the final dx (bias gradient of the Linear that produced x's
+                       residual branch, fused here because this kernel is the producer of that dY) */
 } sc_ln_bwd_desc;
 int sc_layernorm_bwd(const sc_ln_bwd_desc* d, void* stream);
 

@@ -68,6 +68,7 @@ int sc_gemm(const sc_gemm_desc* d, void* stream) {
     if (rc) return rc;
   }
   if (d->in_dtype == SC_BF16 && !d->force_simt) return sc_gemm_tc(d, st);
+  SC_CHECK_ARG(!d->colsum_out, "sc_gemm: colsum_out is only available on the bf16 tensor-core path");
   SC_CHECK_ARG(d->in_dtype == SC_F32 || d->in_dtype == SC_BF16, "sc_gemm: bad in_dtype %d", d->in_dtype);
   return sc_gemm_simt(d, st);
 }

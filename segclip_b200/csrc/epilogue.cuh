@@ -24,6 +24,7 @@ struct EpiParams {
   const void* mul_aux;  // optional: v *= act'(mul_aux[m,n]) (fused activation backward), leading dim ldc
   int mul_aux_dtype;
   int mul_aux_act;
+  float* colsum_out;
 };
 
 static inline EpiParams make_epi(const sc_gemm_desc* d) {
@@ -49,6 +50,7 @@ static inline EpiParams make_epi(const sc_gemm_desc* d) {
   p.mul_aux = d->mul_aux;
   p.mul_aux_dtype = d->mul_aux_dtype;
   p.mul_aux_act = d->mul_aux_act;
+  p.colsum_out = d->colsum_out;
   return p;
 }
 

@@ -101,6 +101,7 @@ int sc_select_epilogue(const sc_gemm_desc* d, int splits) {
   using namespace tc;
   int ef = EF_GENERIC;
   const bool simple = d->alpha == 1.0f && !d->rowbias && (!d->accumulate || splits > 1);
+  // colsum_out is implemented by the bf16-output epilogues only (checked by the caller below)
   if (simple) {
     const bool bias = d->bias != nullptr, resid = d->residual != nullptr, c2 = d->C2 != nullptr, aux = d->mul_aux != nullptr;
     const bool out_bf16 = d->c_dtype == SC_BF16;
@@ -371,6 +372,10 @@ int sc_gemm_tc(const sc_gemm_desc* d, cudaStream_t st) {
   if (rc) return rc;
 
   const int ef = sc_select_epilogue(d, splits);
+  if (d->colsum_out && (ef == EF_GENERIC || (ef & (EF_OUT_F32 | EF_ATOMIC | EF_RESID)) != 0 || ((uintptr_t)d->colsum_out & 15) != 0)) {
+    sc_set_error("sc_gemm: colsum_out needs a bf16-output specialised epilogue and a 16-byte aligned pointer");
+    return SC_ERR_UNSUPPORTED;
+  }
   sc_count_launch(1);
 #define SC_L(BN_, A_, B_, EF_) return launch<BN_, A_, B_, EF_>(d, ta, tb, splits, st);
 #define SC_DISPATCH(BN_)                                                                     \

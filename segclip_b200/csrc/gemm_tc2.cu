@@ -262,6 +262,10 @@ int sc_gemm_tc2(const sc_gemm_desc* d, cudaStream_t st) {
   else rc = sc_get_tensor_map(d->B, d->N, d->K, d->ldb, 64, BK, &tb);
   if (rc) return rc;
   const int ef = sc_select_epilogue(d, splits);
+  if (d->colsum_out && (ef == EF_GENERIC || (ef & (EF_OUT_F32 | EF_ATOMIC | EF_RESID)) != 0 || ((uintptr_t)d->colsum_out & 15) != 0)) {
+    sc_set_error("sc_gemm: colsum_out needs a bf16-output specialised epilogue and a 16-byte aligned pointer");
+    return SC_ERR_UNSUPPORTED;
+  }
   sc_count_launch(1);
 #define SC_L2(A_, B_, EF_) return launch2<A_, B_, EF_>(d, ta, tb, splits, st);
   if (!a_mn && !b_mn) {

@@ -258,6 +258,9 @@ SC_DEVINL void epi_finish(const EpiParams& ep, float (&v)[32], uint32_t stage, i
     __syncwarp();
     // ---- transposed, coalesced stores: 4 lanes x 16 B cover the 64 B of one row, 8 rows per instruction
     const int c = lane & 3, n = n0 + c * 8;
+    float cs[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) cs[k] = 0.f;
 #pragma unroll
     for (int t = 0; t < 4; ++t) {
       const int row = 8 * t + (lane >> 2);
@@ -281,6 +284,28 @@ SC_DEVINL void epi_finish(const EpiParams& ep, float (&v)[32], uint32_t stage, i
           u = make_uint4(uw[0], uw[1], uw[2], uw[3]);
         }
         *(uint4*)((bf16*)ep.C + off) = u;
+        if (ep.colsum_out) {                          // uniform branch: column sums of what was stored
+          const uint32_t uw2[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const float2 x = unpack2_bf16(uw2[k]);
+            cs[2 * k] += x.x;
+            cs[2 * k + 1] += x.y;
+          }
+        }
+      }
+    }
+    if (ep.colsum_out) {
+      // reduce over the 8 row groups of the warp (lanes with equal lane & 3), then one vector reduction per 4 columns
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        cs[k] += __shfl_xor_sync(0xffffffffu, cs[k], 4);
+        cs[k] += __shfl_xor_sync(0xffffffffu, cs[k], 8);
+        cs[k] += __shfl_xor_sync(0xffffffffu, cs[k], 16);
+      }
+      if (lane < 4 && n < ep.N) {
+        asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(ep.colsum_out + n), "f"(cs[0]), "f"(cs[1]), "f"(cs[2]), "f"(cs[3]) : "memory");
+        asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(ep.colsum_out + n + 4), "f"(cs[4]), "f"(cs[5]), "f"(cs[6]), "f"(cs[7]) : "memory");
       }
     }
   } else {

@@ -80,13 +80,15 @@ __global__ void __launch_bounds__(256) ln_fwd_kernel(sc_ln_desc d) {
 // kernel stays under ~80 registers so three CTAs (24 warps) are resident per SM and enough reads are in flight for HBM.
 template <typename TDY, typename TX, typename TDX, int NV>
 __global__ void __launch_bounds__(256, 3) ln_bwd_kernel(sc_ln_bwd_desc d) {
-  extern __shared__ __align__(16) float sacc[];          // [8 warps][2][D]
+  extern __shared__ __align__(16) float sacc[];          // [8 warps][3][D]: dgamma, dbeta, colsum(dx)
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int D4 = d.D >> 2;
   const bool want_param = d.dgamma != nullptr;
-  float* mine = sacc + (size_t)warp * 2 * d.D;
-  if (want_param) {
-    for (int i = lane; i < 2 * d.D; i += 32) mine[i] = 0.f;
+  const bool want_cs = d.dx_colsum != nullptr;
+  const int nacc = want_cs ? 3 : 2;                      // arrays per warp (the colsum slice only when requested)
+  float* mine = sacc + (size_t)warp * nacc * d.D;
+  if (want_param || want_cs) {
+    for (int i = lane; i < nacc * d.D; i += 32) mine[i] = 0.f;
     __syncwarp();
   }
   const bool acc = d.dx && d.accumulate_dx;
@@ -139,17 +141,25 @@ __global__ void __launch_bounds__(256, 3) ln_bwd_kernel(sc_ln_bwd_desc d) {
           o.w = rstd * (dv[j].w * gm.w - c1 - xv[j].w * c2) + old[j].w;
           store4<TDX>(dx, i4, o);
           if (d.dx_copy_bf16) store4<bf16>((bf16*)d.dx_copy_bf16 + row * d.D, i4, o);
+          if (want_cs) {
+            float4* sc = (float4*)(mine + 2 * d.D + i4 * 4);
+            float4 a = *sc;
+            a.x += o.x; a.y += o.y; a.z += o.z; a.w += o.w;
+            *sc = a;
+          }
         }
       }
     }
   }
-  if (!want_param) return;
+  if (!want_param && !want_cs) return;
   __syncthreads();
-  for (int i = threadIdx.x; i < 2 * d.D; i += 256) {
+  for (int i = threadIdx.x; i < nacc * d.D; i += 256) {
+    float* dst = i < d.D ? d.dgamma : (i < 2 * d.D ? d.dbeta : d.dx_colsum);
+    if (dst == nullptr) continue;
     float s = 0.f;
 #pragma unroll
-    for (int w = 0; w < 8; ++w) s += sacc[(size_t)w * 2 * d.D + i];
-    atomicAdd((i < d.D ? d.dgamma : d.dbeta - d.D) + i, s);
+    for (int w = 0; w < 8; ++w) s += sacc[(size_t)w * nacc * d.D + i];
+    atomicAdd(dst + (i % d.D), s);
   }
 }
 
@@ -177,11 +187,11 @@ int launch_bwd(const sc_ln_bwd_desc& d, cudaStream_t st) {
   const int nv = ceil_div(d.D, 128);
   long g = ceil_div(d.rows, 8);
   const int grid = (int)(g < 3L * sc_num_sms() ? g : 3L * sc_num_sms());      // three resident CTAs per SM
-  const size_t smem = d.dgamma ? (size_t)8 * 2 * d.D * sizeof(float) : 0;
+  const size_t smem = d.dx_colsum ? (size_t)8 * 3 * d.D * sizeof(float) : (d.dgamma ? (size_t)8 * 2 * d.D * sizeof(float) : 0);
 #define SC_LN_CASE(NV_)                                                                                      \
   {                                                                                                          \
     static bool cfg = false;                                                                                 \
-    if (!cfg) { cudaFuncSetAttribute(ln_bwd_kernel<TDY, TX, TDX, NV_>, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536); cfg = true; } \
+    if (!cfg) { cudaFuncSetAttribute(ln_bwd_kernel<TDY, TX, TDX, NV_>, cudaFuncAttributeMaxDynamicSharedMemorySize, 98304); cfg = true; } \
     ln_bwd_kernel<TDY, TX, TDX, NV_><<<grid, 256, smem, st>>>(d);                                           \
   }
   switch (nv) {
@@ -221,6 +231,7 @@ extern "C" int sc_layernorm_bwd(const sc_ln_bwd_desc* d, void* stream) {
   SC_CHECK_ARG(d && d->x && d->dy && d->gamma && d->mean && d->rstd, "sc_layernorm_bwd: null pointer");
   SC_CHECK_ARG(d->D % 4 == 0 && d->D > 0, "sc_layernorm_bwd: D=%d must be a multiple of 4", d->D);
   SC_CHECK_ARG((d->dgamma == nullptr) == (d->dbeta == nullptr), "sc_layernorm_bwd: dgamma/dbeta must come together");
+  SC_CHECK_ARG(!d->dx_colsum || d->dx, "sc_layernorm_bwd: dx_colsum needs dx");
   if (d->rows <= 0) return SC_OK;
   sc_count_launch(1);
   const int key = d->dy_dtype * 4 + d->x_dtype * 2 + d->dx_dtype;

@@ -62,7 +62,9 @@ class Plan:
         self.fwd.append(op)
 
     def b(self, group):
-        self.bwd_groups.append(list(group))
+        group = list(group)
+        self.bwd_groups.append(group)
+        return group
 
     def finish(self):
         self.bwd = [op for grp in reversed(self.bwd_groups) for op in grp]
@@ -251,7 +253,8 @@ class Engine:
         center_idx = torch.arange(G, device=dev, dtype=i32).repeat(B)
 
         # ---------------- generic layers
-        def linear_bwd(dy, x, wname, bname, dx=None, dx_acc=False, wslice=None, bslice=None, mul_aux=None, mul_act=0):
+        def linear_bwd(dy, x, wname, bname, dx=None, dx_acc=False, wslice=None, bslice=None, mul_aux=None, mul_act=0,
+                       dx_colsum=None):
             w = self.W(wname)
             gw = self.Gr(wname)
             gb = self.grads[bname] if bname else None
@@ -261,7 +264,8 @@ class Engine:
                 gb = gb[bslice]
             grp = []
             if dx is not None:
-                grp.append(ops.gemm_op(dy, w, dx, trans_b=True, accumulate=dx_acc, mul_aux=mul_aux, mul_aux_act=mul_act))
+                grp.append(ops.gemm_op(dy, w, dx, trans_b=True, accumulate=dx_acc, mul_aux=mul_aux, mul_aux_act=mul_act,
+                                       colsum_out=dx_colsum))
             grp.append(ops.gemm_op(dy, x, gw, trans_a=True, trans_b=True, accumulate=True, split_k=-1))
             if gb is not None:
                 grp.append(ops.colsum_op(dy, gb))
@@ -273,12 +277,12 @@ class Engine:
             pl.f(ops.layernorm_op(x, self.P(pre + ".weight"), self.P(pre + ".bias"), y, eps, mean, rstd, remap))
             return mean, rstd
 
-        def ln_bwd(dy, x, stats, pre, dx=None, acc=False, dx_copy=None, remap=None):
+        def ln_bwd(dy, x, stats, pre, dx=None, acc=False, dx_copy=None, remap=None, colsum=None):
             return ops.layernorm_bwd_op(dy, x, stats[0], stats[1], self.P(pre + ".weight"), dx, acc,
                                         dx_copy if is_bf16 else None, self.grads[pre + ".weight"], self.grads[pre + ".bias"],
-                                        remap)
+                                        remap, colsum)
 
-        def mlp(x_mid, x_out, dx, dxT, pre, nm, tag, eps, act):
+        def mlp(x_mid, x_out, dx, dxT, pre, nm, tag, eps, act, bo_grad=None):
             """x_out = x_mid + W2 act(W1 LN2(x_mid) + b1) + b2; backward leaves d x_mid in dx/dxT."""
             M, D = x_mid.shape
             Dh = self.params[pre + nm["w1"]].shape[0]
@@ -292,12 +296,14 @@ class Engine:
                 grp = linear_bwd(dxT, hact, pre + nm["w2"], pre + nm["b2"], dx=d_a)
                 grp.append(ops.act_bwd_op(d_a, hpre, d_a, act))
             else:
-                grp = linear_bwd(dxT, hact, pre + nm["w2"], pre + nm["b2"], dx=d_a, mul_aux=hpre, mul_act=act)  # fused act'()
-            grp += linear_bwd(d_a, h2, pre + nm["w1"], pre + nm["b1"], dx=d_ln)
-            grp.append(ln_bwd(d_ln, x_mid, st2, pre + nm["ln2"], dx, True, dxT))
+                grp = linear_bwd(dxT, hact, pre + nm["w2"], pre + nm["b2"], dx=d_a, mul_aux=hpre, mul_act=act,  # fused act'()
+                                 dx_colsum=self.grads[pre + nm["b1"]] if is_bf16 else None)                    # + c_fc bias grad
+            fused_b1 = is_bf16 and not os.environ.get("SC_NO_FUSE_ACT")
+            grp += linear_bwd(d_a, h2, pre + nm["w1"], None if fused_b1 else pre + nm["b1"], dx=d_ln)
+            grp.append(ln_bwd(d_ln, x_mid, st2, pre + nm["ln2"], dx, True, dxT, colsum=bo_grad))
             return grp
 
-        def block(x_in, dx, dxT, pre, nm, tag, Bn, Lseq, H, causal=False, eps=1e-5, act=ops.ACT_QUICKGELU):
+        def block(x_in, dx, dxT, pre, nm, tag, Bn, Lseq, H, causal=False, eps=1e-5, act=ops.ACT_QUICKGELU, prev=None):
             """Pre-LN residual block (module_seg_vit.py:191-196, module_clip_ttransformer.py:48-52,
             module_mae.py:199-201).  dx/dxT: gradient of the stream (fp32 + compute-dtype twin)."""
             M, D = x_in.shape
@@ -314,15 +320,25 @@ class Engine:
             x_mid = buf(tag + ".x_mid", (M, D))
             pl.f(ops.gemm_op(att, self.W(pre + nm["wo"]), x_mid, bias=self.P(pre + nm["bo"]), residual=x_in))
             x_out = buf(tag + ".x_out", (M, D))
-            grp_mlp = mlp(x_mid, x_out, dx, dxT, pre, nm, tag, eps, act)
+            # bias gradients that are column sums of a residual-stream gradient are produced by the LayerNorm backward
+            # that writes that gradient: LN2-bwd -> out_proj bias of this block, LN1-bwd -> c_proj bias of the previous block
+            # (measured on B200: +1.15 ms of LN-backward time for 0.6 ms of removed colsum kernels -> off by default)
+            fuse_ln = bool(os.environ.get("SC_FUSE_LN_COLSUM"))
+            grp_mlp = mlp(x_mid, x_out, dx, dxT, pre, nm, tag, eps, act, bo_grad=self.grads[pre + nm["bo"]] if fuse_ln else None)
             d_att, dqkv, d_ln = sbuf("d_att", (M, D), T), sbuf("dqkv", (M, 3 * D), T), sbuf("d_ln", (M, D), T)
-            grp = linear_bwd(dxT, att, pre + nm["wo"], pre + nm["bo"], dx=d_att)
+            grp = linear_bwd(dxT, att, pre + nm["wo"], None if fuse_ln else pre + nm["bo"], dx=d_att)
             grp.append(ops.attention_bwd_op(ad, d_att, dqkv, dqkv[:, D:], dqkv[:, 2 * D:], sbuf("att_delta", (Bn, H, Lseq), f32)))
             grp += linear_bwd(dqkv, h1, pre + nm["wqkv"], pre + nm["bqkv"], dx=d_ln)
-            grp.append(ln_bwd(d_ln, x_in, st1, pre + nm["ln1"], dx, True, dxT))
+            prev_b2 = None
+            if prev is not None and fuse_ln:          # take over the previous block's c_proj bias gradient
+                prev["group"].remove(prev["colsum"])
+                prev_b2 = prev["b2"]
+            grp.append(ln_bwd(d_ln, x_in, st1, pre + nm["ln1"], dx, True, dxT, colsum=prev_b2))
             pl.b(grp)          # executed after the MLP group (groups run in reverse order)
-            pl.b(grp_mlp)
-            return x_out
+            stored = pl.b(grp_mlp)
+            b2_colsum = [op for op in stored if op.name == "sc_colsum"][0]      # colsum(dxT -> c_proj bias)
+            handle = dict(group=stored, colsum=b2_colsum, b2=self.grads[pre + nm["b2"]])
+            return x_out, handle
 
         def cross_block(q_in, xp, dq, dqT, d_xp, pre, tag, Bn, Lx):
             """CrossAttentionBlock (module_seg_vit.py:213-218) incl. both K/V layouts."""
@@ -452,8 +468,10 @@ class Engine:
                                self.Tctx, W_))
         dxt = buf("t.dx", (Mt, W_), zero=True)
         dxtT = tcopy("t.dxT", dxt)
+        hd_ = None
         for i in range(self.text_layers):
-            xt = block(xt, dxt, dxtT, f"clip.transformer.resblocks.{i}.", CLIP_BLOCK, f"t{i}", B, self.Tctx, self.Ht, True)
+            xt, hd_ = block(xt, dxt, dxtT, f"clip.transformer.resblocks.{i}.", CLIP_BLOCK, f"t{i}", B, self.Tctx, self.Ht, True,
+                            prev=hd_)
         xe = buf("t.xe", (B, W_))
         pl.f(ops.gather_rows_op(xt, eot, xe))
         he = buf("t.he", (B, W_), T)
@@ -476,8 +494,9 @@ class Engine:
         Mv = B * self.Lp
         dxv = buf("v.dx", (Mv, D), zero=True)          # gradient of the layers0 stream (many contributors)
         dxvT = tcopy("v.dxT", dxv)
+        hd_ = None
         for i in range(self.fsl):
-            xv = block(xv, dxv, dxvT, f"{t_}layers0.{i}.", CLIP_BLOCK, f"v{i}", B, self.Lp, self.Hv)
+            xv, hd_ = block(xv, dxv, dxvT, f"{t_}layers0.{i}.", CLIP_BLOCK, f"v{i}", B, self.Lp, self.Hv, prev=hd_)
         pl.b(sync_T(dxv, dxvT))        # semantic backward accumulated into dxv; refresh the twin
         d_hard_kl = buf("v.d_hard_kl", (B, G, self.Lp)) if self.use_kl else None
         sx, d_sx, idx_main = semantic(xv, dxv, u1, forced_main, d_hard_kl, "v.sem", B, self.Lp)
@@ -486,8 +505,9 @@ class Engine:
         dc, c = d_sx, sx
         dcT = tcopy("v.dcT", dc)
         pl.b(sync_T(dc, dcT) if self.n2 == 0 else [])
+        hd_ = None
         for i in range(self.n2):
-            c = block(c, dc, dcT, f"{t_}layers2.{i}.", CLIP_BLOCK, f"v2_{i}", B, G, self.Hv)
+            c, hd_ = block(c, dc, dcT, f"{t_}layers2.{i}.", CLIP_BLOCK, f"v2_{i}", B, G, self.Hv, prev=hd_)
         pooled, parg = buf("v.pooled", (B, D)), buf("v.parg", (B, D), i32)
         pl.f(ops.pool_max_op(c, pooled, parg, B, G, D))
         pl.f("force_pool")      # test hook: teacher-forced arg-max routing of the max pooling
@@ -554,8 +574,9 @@ class Engine:
             Mm = B * Lm
             dxm = buf("m.dx", (Mm, D), zero=True)
             dxmT = tcopy("m.dxT", dxm)
+            hd_ = None
             for i in range(self.fsl):
-                xm = block(xm, dxm, dxmT, f"{t_}layers0.{i}.", CLIP_BLOCK, f"m{i}", B, Lm, self.Hv)
+                xm, hd_ = block(xm, dxm, dxmT, f"{t_}layers0.{i}.", CLIP_BLOCK, f"m{i}", B, Lm, self.Hv, prev=hd_)
             pl.b(sync_T(dxm, dxmT))
             d_hard_rec = buf("m.d_hard_rec", (B, G, Lm))
             sxm, d_sxm, idx_mae = semantic(xm, dxm, u3, forced_mae, d_hard_rec, "m.sem", B, Lm)
@@ -567,8 +588,9 @@ class Engine:
             pl.b([ops.reconstruct_bwd_op(dr, rpre, sxm, idx_mae, self.P(r + "weight"), self.P(r + "bias"), d_sxm, d_hard_rec,
                                          self.grads[r + "weight"], self.grads[r + "bias"], B, Lm, D)])
             y = rout
+            hd_ = None
             for i in range(self.n2):
-                y = block(y, dr, drT, f"{t_}layers_mae2.{i}.", CLIP_BLOCK, f"m2_{i}", B, Lm, self.Hv)
+                y, hd_ = block(y, dr, drT, f"{t_}layers_mae2.{i}.", CLIP_BLOCK, f"m2_{i}", B, Lm, self.Hv, prev=hd_)
             m_ = "vis_mae_decoder."
             dd = self.dd
             hc = buf("m.hc", (B * keep, D), T)
@@ -586,9 +608,10 @@ class Engine:
             grp.append(ops.mean_cat_bwd_op(d_hc, dr, B, Lm, D))
             grp += sync_T(dr, drT)
             pl.b(grp)
+            hd_ = None
             for i in range(DEC_DEPTH):
-                xd = block(xd, dxd, dxdT, f"{m_}decoder_blocks.{i}.", MAE_BLOCK, f"md{i}", B, L1, DEC_HEADS, False, 1e-6,
-                           ops.ACT_GELU_ERF)
+                xd, hd_ = block(xd, dxd, dxdT, f"{m_}decoder_blocks.{i}.", MAE_BLOCK, f"md{i}", B, L1, DEC_HEADS, False, 1e-6,
+                                ops.ACT_GELU_ERF, prev=hd_)
             hn = buf("m.hn", (B * L1, dd), T)
             st_dn = ln_fwd(xd, m_ + "decoder_norm", hn, "m.dec_norm", 1e-6)
             Pp = 3 * self.patch * self.patch

@@ -36,7 +36,7 @@ def _p(t):
 
 def gemm_desc(A, B, C_, *, trans_a=False, trans_b=False, bias=None, rowbias=None, rowbias_idx=None, rowbias_mod=0,
               act=ACT_NONE, residual=None, C2=None, accumulate=False, split_k=0, alpha=1.0, force_simt=False,
-              mul_aux=None, mul_aux_act=ACT_NONE):
+              mul_aux=None, mul_aux_act=ACT_NONE, colsum_out=None):
     """sc_gemm descriptor for C = epi(A B^T); see include/segclip_b200.h."""
     for t in (A, B, C_):
         _chk2d(t)
@@ -79,6 +79,9 @@ def gemm_desc(A, B, C_, *, trans_a=False, trans_b=False, bias=None, rowbias=None
         _chk2d(mul_aux)
         assert mul_aux.shape == C_.shape and mul_aux.stride(0) == C_.stride(0)
         d.mul_aux, d.mul_aux_dtype, d.mul_aux_act = mul_aux.data_ptr(), L.dt(mul_aux), mul_aux_act
+    if colsum_out is not None:
+        assert colsum_out.dtype == torch.float32 and colsum_out.numel() == N and C_.dtype == torch.bfloat16
+        d.colsum_out = colsum_out.data_ptr()
     return d
 
 
@@ -107,7 +110,7 @@ def layernorm_op(x, gamma, beta, y, eps=1e-5, mean=None, rstd=None, remap=None):
 
 
 def layernorm_bwd_op(dy, x, mean, rstd, gamma, dx=None, accumulate_dx=False, dx_copy=None, dgamma=None, dbeta=None,
-                     remap=None):
+                     remap=None, dx_colsum=None):
     rows, D = x.shape
     d = L.LnBwdDesc()
     d.rows, d.D = rows, D
@@ -124,7 +127,10 @@ def layernorm_bwd_op(dy, x, mean, rstd, gamma, dx=None, accumulate_dx=False, dx_
     d.dgamma, d.dbeta = _p(dgamma), _p(dbeta)
     if remap is not None:
         d.in_group, d.out_group, d.out_off = remap
-    return Op("sc_layernorm_bwd", (C.byref(d),), (d, dy, x, mean, rstd, gamma, dx, dx_copy, dgamma, dbeta))
+    if dx_colsum is not None:
+        assert dx_colsum.dtype == torch.float32 and dx_colsum.numel() == D
+        d.dx_colsum = dx_colsum.data_ptr()
+    return Op("sc_layernorm_bwd", (C.byref(d),), (d, dy, x, mean, rstd, gamma, dx, dx_copy, dgamma, dbeta, dx_colsum))
 
 
 def attn_desc(q, k, v, o, lse, B, H, Lq, Lk, hd, q_str, k_str, v_str, o_str, causal=False, force_generic=False):
