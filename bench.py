@@ -25,7 +25,8 @@ import torch
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-GF_PER_PAIR = {False: 110.0, True: 144.4}      # algorithmic GEMM FLOPs, fwd+bwd = 3x fwd
+GF_PER_PAIR = {("vitb16", False): 110.0, ("vitb16", True): 144.4,      # algorithmic GEMM FLOPs, fwd+bwd = 3x fwd
+               ("vitl14", False): 252.0, ("vitl14", True): 330.6}      # ViT-L/14@224 as the reference builds it (10+2 layers)
 METRIC = "image-text pairs/sec (224^2, seq77) fwd+bwd"
 
 
@@ -95,7 +96,7 @@ def run_reference(args):
     from oracle import segclip_oracle as so
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    cfg = so.vit_b16_config(use_mae=args.heads, use_kl=args.heads)
+    cfg = model_config(so, args)
     Bc = args.cpu_batch
     params = so.init_params(cfg, seed=0)
     frozen = ("vis_mae_decoder.decoder_pos_embed",)
@@ -119,9 +120,19 @@ def run_reference(args):
         "e2e": {"value": v, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
 
 
+def model_config(so, args):
+    if args.model == "vitl14":      # BASELINE configs[4]: width 1024 / 16 heads / patch 14, text 768 / 12 heads, E = 768 (F5: 10+2 layers)
+        return so.vit_b16_config(vision_width=1024, text_width=768, embed_dim=768, patch=14, grid=16, use_mae=args.heads,
+                                 use_kl=args.heads)
+    return so.vit_b16_config(use_mae=args.heads, use_kl=args.heads)
+
+
 def workload_name(args):
-    return "ViT-B/16 SegCLIP full fwd+bwd, per-GPU batch %d, %s, bf16 (BASELINE configs[1])" % (
-        args.batch, "contrastive + MAE-recon + superpixel-KL" if args.heads else "contrastive only")
+    name = "ViT-B/16 SegCLIP" if args.model == "vitb16" else "ViT-L/14 (10+2 layers, as the reference builds it) SegCLIP"
+    tag = "BASELINE configs[1]" if (args.model == "vitb16" and not args.heads) else \
+        ("BASELINE configs[3] shape" if args.model == "vitb16" else "BASELINE configs[4] shape")
+    return "%s full fwd+bwd, per-GPU batch %d, %s, bf16 (%s)" % (
+        name, args.batch, "contrastive + MAE-recon + superpixel-KL" if args.heads else "contrastive only", tag)
 
 
 def main():
@@ -135,6 +146,7 @@ def main():
     ap.add_argument("--cpu-batch", type=int, default=16)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--precision", default="bf16")
+    ap.add_argument("--model", default="vitb16", choices=["vitb16", "vitl14"])
     ap.add_argument("--ddp", action="store_true", help="use torch DDP for the gradient mean instead of the native overlapped sync")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl != "reference" else args.warmup
@@ -156,7 +168,7 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
-    cfg = so.vit_b16_config(use_mae=args.heads, use_kl=args.heads)
+    cfg = model_config(so, args)
     tc = argparse.Namespace(local_rank=local, rank=rank, world_size=world, first_stage_layer=10,
                             use_vision_mae_recon=args.heads, use_seglabel=args.heads, precision=args.precision)
     torch.manual_seed(0)
@@ -219,7 +231,7 @@ def main():
         return
     pk = peaks()
     value = B * world / (ms / 1e3)
-    gf = GF_PER_PAIR[args.heads]
+    gf = GF_PER_PAIR[(args.model, args.heads)]
     out = {
         "metric": METRIC, "value": value, "unit": "pairs/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
@@ -248,7 +260,7 @@ def main():
 def cpu_baseline(so, args):
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    cfg = so.vit_b16_config(use_mae=args.heads, use_kl=args.heads)
+    cfg = model_config(so, args)
     Bc = args.cpu_batch
     params = so.init_params(cfg, seed=0)
     batch, noise = so.make_batch(cfg, Bc, seed=0)

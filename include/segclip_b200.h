@@ -215,10 +215,11 @@ int sc_blockdiag_expand(const float* w, void* dense, int C, int groups, int dtyp
 int sc_blockdiag_reduce(const float* dense_grad, float* dw, int C, int groups, void* stream);
 
 /* Non-overlapping patch extraction for conv1 (kernel == stride, module_clip_vtransformer.py:21,56):
- * out[r, c*p*p + y*p + x] = image[r / rows_per_img, c, (pid / grid)*p + y, (pid % grid)*p + x],
- * pid = patch_idx ? patch_idx[r] : r % rows_per_img (MAE pass: only kept patches are embedded). */
-int sc_im2col(const float* image, void* out, int out_dtype, const int32_t* patch_idx, int64_t rows, int rows_per_img,
-              int grid, int patch, void* stream);
+ * out[r*ld + c*p*p + y*p + x] = image[r / rows_per_img, c, (pid / grid)*p + y, (pid % grid)*p + x],
+ * pid = patch_idx ? patch_idx[r] : r % rows_per_img (MAE pass: only kept patches are embedded).
+ * ld >= 3*p*p is the row pitch of `out` (padded to a multiple of 8 for TMA when 3*p*p is not, e.g. patch 14). */
+int sc_im2col(const float* image, void* out, int out_dtype, int64_t ld, const int32_t* patch_idx, int64_t rows,
+              int rows_per_img, int grid, int patch, void* stream);
 
 /* token_embedding(ids) + positional_embedding (modules/module_clip.py:109-112) and the flat row index
  * b*T + argmax_t ids[b,t] of the EOT token (:136). */
@@ -361,6 +362,33 @@ int sc_p2p_free(void* buf, void* pad);
 int sc_p2p_allgather(int nseg, const void* const* srcs, const int64_t* nbytes, const int64_t* offs, void* const* peer_bufs,
                      void* const* peer_pads, int rank, int world, uint32_t epoch, void* scratch, void* stream);
 int sc_p2p_release(void* const* peer_pads, int rank, int world, uint32_t epoch, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * "Next" row: fused optimizer step = torch.nn.utils.clip_grad_norm_(params, max_norm)
+ * (main_task_align.py:326) + AdaptAdamW.step (modules/optimization_adamw.py:112-174: decoupled weight decay BEFORE the
+ * Adam update, bias-corrected step size and denominator) + the logit_scale clamp (main_task_align.py:343-347).
+ * One table entry per parameter tensor; per-tensor scalars are computed on the host from the group's step count and
+ * cosine-warm-up schedule:  decay = 1 - lr*wd,  step_size = lr / (1 - b1^t),  inv_sqrt_bc2 = 1 / sqrt(1 - b2^t).
+ *   sc_grad_sqnorm_multi: *out_sqnorm += sum over all tensors of ||grad||^2     (caller zeroes out_sqnorm)
+ *   sc_adamw_multi      : g' = g * min(1, max_norm/(sqrt(*sqnorm)+1e-6));  m,v update;  p = p*decay - step_size*m/(sqrt(v)*inv_sqrt_bc2+eps)
+ */
+typedef struct {
+  void* param;        /* fp32, updated in place */
+  const void* grad;   /* fp32 or NULL (tensor skipped, like `if p.grad is None: continue`) */
+  void* exp_avg;      /* fp32 state */
+  void* exp_avg_sq;   /* fp32 state */
+  int64_t n;
+  int64_t first_block; /* prefix sum of ceil(n / 1024) */
+  float decay;
+  float step_size;
+  float inv_sqrt_bc2;
+  float clamp_max;
+  int32_t clamp_max_enabled;
+  int32_t pad_;
+} sc_opt_item;
+int sc_grad_sqnorm_multi(const sc_opt_item* items_dev, int n_items, int64_t total_blocks, float* out_sqnorm, void* stream);
+int sc_adamw_multi(const sc_opt_item* items_dev, int n_items, int64_t total_blocks, const float* sqnorm, float max_norm,
+                   float beta1, float beta2, float eps, void* stream);
 
 #ifdef __cplusplus
 }

@@ -90,6 +90,7 @@ AttnBwdDesc = STRUCTS["sc_attn_bwd_desc"]
 CastItem = STRUCTS["sc_cast_item"]
 AssignDesc = STRUCTS["sc_assign_desc"]
 AssignBwdDesc = STRUCTS["sc_assign_bwd_desc"]
+OptItem = STRUCTS["sc_opt_item"]
 
 _lib = None
 

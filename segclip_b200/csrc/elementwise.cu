@@ -131,7 +131,7 @@ __global__ void blockdiag_reduce_kernel(const float* __restrict__ dense, float* 
 
 // ---------------------------------------------------------------- patch extraction (im2col for stride == kernel)
 template <typename T>
-__global__ void im2col_kernel(const float* __restrict__ img, T* __restrict__ out, const int* __restrict__ patch_idx,
+__global__ void im2col_kernel(const float* __restrict__ img, T* __restrict__ out, long ld, const int* __restrict__ patch_idx,
                               int rows_per_img, int grid, int p, int res) {
   const long row = blockIdx.x;
   const int b = row / rows_per_img;
@@ -140,7 +140,7 @@ __global__ void im2col_kernel(const float* __restrict__ img, T* __restrict__ out
   const int K = 3 * p * p;
   for (int k = threadIdx.x; k < K; k += blockDim.x) {
     int c = k / (p * p), r = (k / p) % p, q = k % p;
-    out[row * K + k] = from_f32<T>(img[(((long)b * 3 + c) * res + py0 + r) * res + px0 + q]);
+    out[row * ld + k] = from_f32<T>(img[(((long)b * 3 + c) * res + py0 + r) * res + px0 + q]);
   }
 }
 
@@ -315,14 +315,14 @@ int sc_blockdiag_reduce(const float* dense_grad, float* dw, int C, int groups, v
   return SC_OK;
 }
 
-int sc_im2col(const float* image, void* out, int out_dtype, const int32_t* patch_idx, int64_t rows, int rows_per_img,
-              int grid, int patch, void* stream) {
-  SC_CHECK_ARG(image && out && rows > 0, "sc_im2col: bad args");
+int sc_im2col(const float* image, void* out, int out_dtype, int64_t ld, const int32_t* patch_idx, int64_t rows,
+              int rows_per_img, int grid, int patch, void* stream) {
+  SC_CHECK_ARG(image && out && rows > 0 && ld >= 3 * patch * patch, "sc_im2col: bad args");
   sc_count_launch(1);
   if (out_dtype == SC_F32)
-    im2col_kernel<float><<<(unsigned)rows, 256, 0, (cudaStream_t)stream>>>(image, (float*)out, patch_idx, rows_per_img, grid, patch, grid * patch);
+    im2col_kernel<float><<<(unsigned)rows, 256, 0, (cudaStream_t)stream>>>(image, (float*)out, ld, patch_idx, rows_per_img, grid, patch, grid * patch);
   else
-    im2col_kernel<bf16><<<(unsigned)rows, 256, 0, (cudaStream_t)stream>>>(image, (bf16*)out, patch_idx, rows_per_img, grid, patch, grid * patch);
+    im2col_kernel<bf16><<<(unsigned)rows, 256, 0, (cudaStream_t)stream>>>(image, (bf16*)out, ld, patch_idx, rows_per_img, grid, patch, grid * patch);
   SC_LAUNCH_CHECK();
   return SC_OK;
 }

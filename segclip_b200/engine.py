@@ -198,6 +198,21 @@ class Engine:
         t = self.shadow[name] if name in self.shadow else self.params[name].data
         return t.reshape(t.shape[0], -1)
 
+    def conv_weight(self):
+        """conv1 weight as a [width, 3*p*p (padded to a multiple of 8)] GEMM operand in the compute dtype."""
+        w = self.W("clip.visual.conv1.weight")
+        K = w.shape[1]
+        if K % 8 == 0:
+            return w
+        if getattr(self, "_conv_pad", None) is None:
+            self._conv_pad = torch.zeros(w.shape[0], (K + 7) // 8 * 8, device=self.dev, dtype=self.T)
+        return self._conv_pad
+
+    def _refresh_conv_pad(self):
+        if getattr(self, "_conv_pad", None) is not None:
+            w = self.W("clip.visual.conv1.weight")
+            self._conv_pad[:, :w.shape[1]].copy_(w)      # frozen stem weight: a strided copy, no arithmetic
+
     def Gr(self, name):
         g = self.grads[name]
         return g.reshape(g.shape[0], -1) if g.dim() >= 2 else g
@@ -447,12 +462,14 @@ class Engine:
             v = "clip.visual."
             M = B * rows_per_img
             K = 3 * self.patch * self.patch
-            cols = buf(tag + ".cols", (M, K), T)
+            Kp = (K + 7) // 8 * 8          # TMA needs 16-byte row pitches: patch 14 -> 588 -> 592 (zero padded)
+            cols = buf(tag + ".cols", (M, Kp), T, zero=(Kp != K))
+            if Kp != K:
+                pl.zero.remove(cols)       # the padding columns are zeroed once, im2col never touches them
             pl.f(ops.im2col_op(image, cols, patch_idx, rows_per_img, self.grid, self.patch))
             pre = buf(tag + ".pre", (M, self.vw))
             pos = self.P(v + "positional_embedding")[1:]
-            pl.f(ops.gemm_op(cols, self.W(v + "conv1.weight"), pre, rowbias=pos, rowbias_idx=patch_idx,
-                             rowbias_mod=self.Lp))
+            pl.f(ops.gemm_op(cols, self.conv_weight(), pre, rowbias=pos, rowbias_idx=patch_idx, rowbias_mod=self.Lp))
             x0 = buf(tag + ".x0", (M, self.vw))
             pl.f(ops.layernorm_op(pre, self.P(v + "ln_pre.weight"), self.P(v + "ln_pre.bias"), x0))
             return x0
@@ -718,6 +735,7 @@ class Engine:
             self.cast_op(st)
         for op in self.prep_ops:
             op(st)
+        self._refresh_conv_pad()
         for op in pl.fwd:
             if isinstance(op, str):
                 if op == "force_pool":

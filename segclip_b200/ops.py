@@ -198,8 +198,8 @@ def blockdiag_reduce_op(dense_grad, dw, groups):
 
 
 def im2col_op(image, out, patch_idx, rows_per_img, grid, patch):
-    return Op("sc_im2col", (image.data_ptr(), out.data_ptr(), L.dt(out), _p(patch_idx), out.shape[0], rows_per_img, grid,
-                            patch), (image, out, patch_idx))
+    return Op("sc_im2col", (image.data_ptr(), out.data_ptr(), L.dt(out), out.stride(0), _p(patch_idx), out.shape[0],
+                            rows_per_img, grid, patch), (image, out, patch_idx))
 
 
 def text_embed_op(ids, tok, pos, out, eot_rows, B, T, W):

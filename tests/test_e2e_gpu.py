@@ -57,6 +57,33 @@ def test_bf16_unforced_loss_and_flip_rates():
     assert r["pool_flip_rate"] <= 0.05, r["pool_flip_rate"]
 
 
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_patch14_geometry_matches_oracle(precision):
+    """ViT-L/14-style geometry (3*14*14 = 588 is not a multiple of 8: padded im2col / conv operand) against the oracle."""
+    import torch
+    from oracle import segclip_oracle as so
+    from segclip_b200.engine import FROZEN_STEM
+    from tools.e2e_report import build_model
+    cfg = so.toy_config(patch=14, grid=4, use_mae=True, use_kl=True)
+    params = so.init_params(cfg, seed=21)
+    batch, noise = so.make_batch(cfg, 3, seed=22)
+    ref_loss, ref_grads, info = so.loss_and_grads(params, batch, noise, cfg, "torch18_flat", frozen=FROZEN_STEM)
+    model = build_model(cfg, params, precision, "torch18_flat")
+    model.inject_noise({k: v.cuda() for k, v in noise.items()})
+    if precision == "bf16":
+        model.force_assignment({"main": info["assign_main"].cuda(), "mae": info["assign_mae"].cuda(), "pool": info["pool_arg"].cuda()})
+    ids = batch["input_ids"]
+    loss = model(ids, torch.zeros_like(ids), batch["attention_mask"], batch["image"], image_seg=batch["image_seg"])
+    loss.backward()
+    tol_l, tol_g = (1e-3, 1e-3) if precision == "fp32" else (1e-2, 0.15)
+    assert abs(float(loss.detach()) - float(ref_loss)) <= tol_l * abs(float(ref_loss))
+    for n, p in model.named_parameters():
+        if n in FROZEN_STEM or p.grad is None:
+            continue
+        g, r = p.grad.float().cpu(), ref_grads[n]
+        assert float((g - r).norm()) <= tol_g * float(r.norm()) + 1e-9, n
+
+
 def test_grad_output_scaling_and_repeatability():
     """loss.backward(gradient=s) scales every gradient by s on the device; two identical steps agree."""
     import argparse
