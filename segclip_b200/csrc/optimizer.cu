@@ -57,6 +57,24 @@ __global__ void __launch_bounds__(256) adamw_kernel(const sc_opt_item* __restric
   float* m = (float*)it.exp_avg;
   float* v = (float*)it.exp_avg_sq;
   const long base = (blk - it.first_block) * 1024 + threadIdx.x * 4;
+  if (base + 3 < it.n && (((uintptr_t)(p + base) | (uintptr_t)(g + base) | (uintptr_t)(m + base) | (uintptr_t)(v + base)) & 15) == 0) {
+    float4 p4 = *(float4*)(p + base), m4 = *(float4*)(m + base), v4 = *(float4*)(v + base);
+    const float4 g4 = *(const float4*)(g + base);
+    float* pp = &p4.x; float* mm = &m4.x; float* vv = &v4.x; const float* gg = &g4.x;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float gi = gg[k] * clip;
+      mm[k] = beta1 * mm[k] + (1.0f - beta1) * gi;
+      vv[k] = beta2 * vv[k] + (1.0f - beta2) * gi * gi;
+      float w = pp[k] * it.decay - it.step_size * (mm[k] / (sqrtf(vv[k]) * it.inv_sqrt_bc2 + eps));
+      if (it.clamp_max_enabled) w = fminf(w, it.clamp_max);
+      pp[k] = w;
+    }
+    *(float4*)(p + base) = p4;
+    *(float4*)(m + base) = m4;
+    *(float4*)(v + base) = v4;
+    return;
+  }
   for (long i = base; i < base + 4 && i < it.n; ++i) {
     const float gi = g[i] * clip;
     const float mi = beta1 * m[i] + (1.0f - beta1) * gi;

@@ -269,7 +269,7 @@ class Engine:
 
         # ---------------- generic layers
         def linear_bwd(dy, x, wname, bname, dx=None, dx_acc=False, wslice=None, bslice=None, mul_aux=None, mul_act=0,
-                       dx_colsum=None):
+                       dx_colsum=None, simt=False):
             w = self.W(wname)
             gw = self.Gr(wname)
             gb = self.grads[bname] if bname else None
@@ -280,8 +280,9 @@ class Engine:
             grp = []
             if dx is not None:
                 grp.append(ops.gemm_op(dy, w, dx, trans_b=True, accumulate=dx_acc, mul_aux=mul_aux, mul_aux_act=mul_act,
-                                       colsum_out=dx_colsum))
-            grp.append(ops.gemm_op(dy, x, gw, trans_a=True, trans_b=True, accumulate=True, split_k=-1))
+                                       colsum_out=dx_colsum, force_simt=simt))
+            grp.append(ops.gemm_op(dy, x, gw, trans_a=True, trans_b=True, accumulate=True, split_k=0 if simt else -1,
+                                   force_simt=simt))
             if gb is not None:
                 grp.append(ops.colsum_op(dy, gb))
             return grp
@@ -465,7 +466,7 @@ class Engine:
             Kp = (K + 7) // 8 * 8          # TMA needs 16-byte row pitches: patch 14 -> 588 -> 592 (zero padded)
             cols = buf(tag + ".cols", (M, Kp), T, zero=(Kp != K))
             if Kp != K:
-                pl.zero.remove(cols)       # the padding columns are zeroed once, im2col never touches them
+                pl.zero[:] = [z for z in pl.zero if z is not cols]      # padding zeroed once; im2col never touches it
             pl.f(ops.im2col_op(image, cols, patch_idx, rows_per_img, self.grid, self.patch))
             pre = buf(tag + ".pre", (M, self.vw))
             pos = self.P(v + "positional_embedding")[1:]
@@ -633,10 +634,14 @@ class Engine:
             st_dn = ln_fwd(xd, m_ + "decoder_norm", hn, "m.dec_norm", 1e-6)
             Pp = 3 * self.patch * self.patch
             pred, dpred = buf("m.pred", (B * L1, Pp), T), buf("m.dpred", (B * L1, Pp), T)
-            pl.f(ops.gemm_op(hn, self.W(m_ + "decoder_pred.weight"), pred, bias=self.P(m_ + "decoder_pred.bias")))
+            # 3*p*p output columns: not a multiple of 8 for patch 14 (588) -> this one layer runs on the exact-FMA kernel
+            # (TMA needs 16-byte row pitches); known slow spot of the ViT-L/14 + MAE configuration
+            pred_simt = Pp % 8 != 0
+            pl.f(ops.gemm_op(hn, self.W(m_ + "decoder_pred.weight"), pred, bias=self.P(m_ + "decoder_pred.bias"),
+                             force_simt=pred_simt))
             pl.f(ops.mae_loss_op(pred, image, mask, loss, dpred, B, L1, keep, self.grid, self.patch))
             d_hn = sbuf("m.d_hn", (B * L1, dd), T)
-            grp = linear_bwd(dpred, hn, m_ + "decoder_pred.weight", m_ + "decoder_pred.bias", dx=d_hn)
+            grp = linear_bwd(dpred, hn, m_ + "decoder_pred.weight", m_ + "decoder_pred.bias", dx=d_hn, simt=pred_simt)
             grp.append(ln_bwd(d_hn, xd, st_dn, m_ + "decoder_norm", dxd, False, dxdT))
             pl.b(grp)
 
