@@ -84,6 +84,19 @@ __global__ void attn_delta_kernel(const bf16* __restrict__ o, const bf16* __rest
   delta[((long)b * H + h) * L + i] = s;
 }
 
+SC_DEVINL void tmem_ld32_nowait(uint32_t taddr, float* v) {
+  uint32_t* r = (uint32_t*)v;
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
 SC_DEVINL void tmem_ld16(uint32_t taddr, float* v) {
   uint32_t* r = (uint32_t*)v;
   asm volatile(
@@ -138,14 +151,18 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     mbar_init(bar_dkv_free, NSOFT);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    // TMA right away: the four operands of this (sample, head) -- rows b*L .. (+ntile*128), columns h*64 .. (+64) --
+    // fly while TMEM is allocated and the lse / delta rows are staged
+    const int box_bytes = ntile * TILE * 128;
+    mbar_expect_tx(bar_load, 4 * box_bytes);
+    tma_load_2d(&tmQ, bar_load, smem + SM_Q, h * HD, b * L);
+    tma_load_2d(&tmK, bar_load, smem + SM_K, h * HD, b * L);
+    tma_load_2d(&tmV, bar_load, smem + SM_V, h * HD, b * L);
+    tma_load_2d(&tmdO, bar_load, smem + SM_DO, h * HD, b * L);
   }
   if (warp == NSOFT) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-    if (lane == 0) {
-      // TMA: the four operands of this (sample, head): rows b*L .. (+ntile*128), columns h*64 .. (+64)
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    }
   }
   for (int i = threadIdx.x; i < ROWS; i += TC_THREADS) {
     const long o = ((long)b * a.H + h) * L + i;
@@ -160,12 +177,6 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
 
   if (warp == NSOFT) {
     if (lane == 0) {
-      const int box_bytes = ntile * TILE * 128;
-      mbar_expect_tx(bar_load, 4 * box_bytes);
-      tma_load_2d(&tmQ, bar_load, smem + SM_Q, h * HD, b * L);
-      tma_load_2d(&tmK, bar_load, smem + SM_K, h * HD, b * L);
-      tma_load_2d(&tmV, bar_load, smem + SM_V, h * HD, b * L);
-      tma_load_2d(&tmdO, bar_load, smem + SM_DO, h * HD, b * L);
       mbar_wait(bar_load, 0);
       tcgen05_fence_after();
       constexpr uint32_t ID_S = make_idesc(128, false, false);   // S, dP : A K-major, B K-major
@@ -242,8 +253,9 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         const bool warp_live = (qt * TILE + quarter * 32 < L) && key0 < L && (!CAUSAL || key0 <= qt * TILE + quarter * 32 + 31);
         if (warp_live) {
           float s[32], dp[32];
-          tmem_ld32(tmem + lane_off + TM_ST + cg * 32, s);
-          tmem_ld32(tmem + lane_off + TM_DPT + cg * 32, dp);
+          tmem_ld32_nowait(tmem + lane_off + TM_ST + cg * 32, s);
+          tmem_ld32_nowait(tmem + lane_off + TM_DPT + cg * 32, dp);
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
           for (int j = 0; j < 32; j += 2) {
             const int k0 = key0 + j;
