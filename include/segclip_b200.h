@@ -221,6 +221,11 @@ int sc_blockdiag_reduce(const float* dense_grad, float* dw, int C, int groups, v
 int sc_im2col(const float* image, void* out, int out_dtype, int64_t ld, const int32_t* patch_idx, int64_t rows,
               int rows_per_img, int grid, int patch, void* stream);
 
+/* "Next" row: uint8 image boundary.  out = (img/255 - mean[c]) / std[c] for a [*, 3, H, W] uint8
+ * batch already on the device (hw = H*W; mean3/std3 are HOST arrays of 3 floats): the normalisation of
+ * dataloaders/rawimage_util.py moved behind the H2D copy, so 1 byte per pixel crosses PCIe instead of 4 (or 8). */
+int sc_u8_normalize(const uint8_t* img, float* out, int64_t n, int hw, const float* mean3, const float* std3, void* stream);
+
 /* token_embedding(ids) + positional_embedding (modules/module_clip.py:109-112) and the flat row index
  * b*T + argmax_t ids[b,t] of the EOT token (:136). */
 int sc_text_embed(const int64_t* ids, const float* tok, const float* pos, float* out, int32_t* eot_rows, int B, int T,

@@ -19,7 +19,7 @@ ACT_NONE, ACT_QUICKGELU, ACT_GELU_ERF = 0, 1, 2
 _DT = {torch.float32: F32, torch.bfloat16: BF16}
 TORCH_DT = {F32: torch.float32, BF16: torch.bfloat16}
 
-_SCALARS = {"int32_t": C.c_int32, "uint32_t": C.c_uint32, "int64_t": C.c_int64, "float": C.c_float, "int": C.c_int,
+_SCALARS = {"int32_t": C.c_int32, "uint32_t": C.c_uint32, "uint8_t": C.c_uint8, "int64_t": C.c_int64, "float": C.c_float, "int": C.c_int,
             "size_t": C.c_size_t, "long long": C.c_longlong}
 
 

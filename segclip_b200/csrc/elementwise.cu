@@ -144,6 +144,27 @@ __global__ void im2col_kernel(const float* __restrict__ img, T* __restrict__ out
   }
 }
 
+// ---------------------------------------------------------------- uint8 image boundary
+// out[b,c,y,x] = (img[b,c,y,x] / 255 - mean[c]) / std[c]: the normalisation the reference loaders do on the host in float64
+// (dataloaders/rawimage_util.py), moved after the H2D copy so only 1 byte per pixel crosses PCIe.
+__global__ void u8_normalize_kernel(const uint8_t* __restrict__ img, float* __restrict__ out, long n, int hw, float m0, float m1,
+                                    float m2, float s0, float s1, float s2) {
+  const long i = ((long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  if (i >= n) return;
+  const int c = (int)((i / hw) % 3);
+  const float m = c == 0 ? m0 : (c == 1 ? m1 : m2), s = c == 0 ? s0 : (c == 1 ? s1 : s2);
+  if (i + 3 < n && (hw & 3) == 0) {
+    const uchar4 u = *(const uchar4*)(img + i);
+    *(float4*)(out + i) = make_float4((u.x / 255.0f - m) / s, (u.y / 255.0f - m) / s, (u.z / 255.0f - m) / s, (u.w / 255.0f - m) / s);
+  } else {
+    for (long j = i; j < i + 4 && j < n; ++j) {
+      const int cj = (int)((j / hw) % 3);
+      const float mj = cj == 0 ? m0 : (cj == 1 ? m1 : m2), sj = cj == 0 ? s0 : (cj == 1 ? s1 : s2);
+      out[j] = (img[j] / 255.0f - mj) / sj;
+    }
+  }
+}
+
 // ---------------------------------------------------------------- text embedding
 __global__ void embed_kernel(const long long* __restrict__ ids, const float* __restrict__ tok,
                              const float* __restrict__ pos, float* __restrict__ out, int T, int W) {
@@ -323,6 +344,15 @@ int sc_im2col(const float* image, void* out, int out_dtype, int64_t ld, const in
     im2col_kernel<float><<<(unsigned)rows, 256, 0, (cudaStream_t)stream>>>(image, (float*)out, ld, patch_idx, rows_per_img, grid, patch, grid * patch);
   else
     im2col_kernel<bf16><<<(unsigned)rows, 256, 0, (cudaStream_t)stream>>>(image, (bf16*)out, ld, patch_idx, rows_per_img, grid, patch, grid * patch);
+  SC_LAUNCH_CHECK();
+  return SC_OK;
+}
+
+int sc_u8_normalize(const uint8_t* img, float* out, int64_t n, int hw, const float* mean3, const float* std3, void* stream) {
+  SC_CHECK_ARG(img && out && n > 0 && hw > 0 && mean3 && std3, "sc_u8_normalize: bad args");
+  sc_count_launch(1);
+  u8_normalize_kernel<<<ceil_div(n, 4 * 256), 256, 0, (cudaStream_t)stream>>>(img, out, n, hw, mean3[0], mean3[1], mean3[2], std3[0],
+                                                                               std3[1], std3[2]);
   SC_LAUNCH_CHECK();
   return SC_OK;
 }

@@ -715,11 +715,15 @@ class Engine:
             cur = torch.cuda.current_stream(self.dev)
             self._copy_stream.wait_stream(cur)           # previous step's readers of in.image are done
             with torch.cuda.stream(self._copy_stream):
-                if img.dtype == torch.float32 and img.dim() == 5:
+                if img.dtype == torch.uint8:
+                    self._upload_u8(img, b["in.image"], inputs["norm"])
+                elif img.dtype == torch.float32 and img.dim() == 5:
                     b["in.image"].copy_(img[:, 0], non_blocking=True)
                 else:
                     b["in.image"].copy_(img.reshape(b["in.image"].shape).to(torch.float32), non_blocking=True)
                 self._img_event = self._copy_stream.record_event()
+        elif img.dtype == torch.uint8:
+            self._upload_u8(img, b["in.image"], inputs["norm"])
         else:
             b["in.image"].copy_(img.reshape(b["in.image"].shape), non_blocking=True)
         if inputs.get("seg") is not None:
@@ -756,6 +760,17 @@ class Engine:
             else:
                 op(st)
         return pl.loss
+
+    def _upload_u8(self, img, dst, norm):
+        """uint8 pixels -> device (1 B/pixel over PCIe) -> normalised fp32 by the native kernel, on the current stream."""
+        import ctypes
+        if getattr(self, "_u8_stage", None) is None or self._u8_stage.numel() != dst.numel():
+            self._u8_stage = torch.empty(dst.numel(), device=self.dev, dtype=torch.uint8)
+        self._u8_stage.copy_(img.reshape(-1), non_blocking=True)
+        mean = (ctypes.c_float * 3)(*norm[0])
+        std = (ctypes.c_float * 3)(*norm[1])
+        L.check(L.lib().sc_u8_normalize(self._u8_stage.data_ptr(), dst.data_ptr(), dst.numel(), dst.shape[-1] * dst.shape[-2],
+                                        mean, std, L.stream()), "sc_u8_normalize")
 
     def backward(self, B):
         pl = self.plan(B)

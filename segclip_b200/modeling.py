@@ -252,6 +252,9 @@ class SegCLIP(nn.Module):
         self._forced = None
         self._exchange = None
         self._sync_group = None
+        # CLIP preprocessing constants (dataloaders/rawimage_util.py Normalize); used only for uint8 image batches
+        self.image_norm = (get_attr(task_config, "image_mean", (0.48145466, 0.4578275, 0.40821073)),
+                           get_attr(task_config, "image_std", (0.26862954, 0.26130258, 0.27577711)))
 
     # ---- reference-compatible constructors ---------------------------------------------------
     @classmethod
@@ -352,7 +355,9 @@ class SegCLIP(nn.Module):
         ids = ids.view(-1, ids.shape[-1]).to(dev, non_blocking=True)
         img = torch.as_tensor(image)
         b, pair, ch, h, w = img.shape
-        if img.device.type != "cpu":
+        if img.dtype == torch.uint8:
+            pass                                   # raw pixels: normalised on the device (CLIP mean / std), see _upload_u8
+        elif img.device.type != "cpu":
             img = img[:, 0].float()                # device input: cast in place of the reference's .float() (modeling.py:182)
         elif img.dtype != torch.float32:
             img = img[:, 0].float()                # float64 host arrays of the reference loaders: cast once on the host
@@ -366,7 +371,7 @@ class SegCLIP(nn.Module):
             if self.cfg["use_mae"]:
                 noise["u2"] = torch.rand(b, c.Lp + 1, device=dev)
                 noise["u3"] = torch.rand(b, G, c.Lm, device=dev)
-        inputs = dict(ids=ids, image=img, seg=seg)
+        inputs = dict(ids=ids, image=img, seg=seg, norm=self.image_norm)
         params = [p for _, p in self._active_items]
         return _NativeStep.apply(self, b, inputs, noise, self._forced, *params)
 

@@ -129,3 +129,26 @@ def test_eval_mode_returns_none_and_cpu_is_refused():
     m.train()
     with pytest.raises(_lib.SegclipB200Error):                          # no CPU fallback
         m(ids, ids, ids, batch["image"])
+
+
+def test_uint8_image_boundary_matches_host_normalisation():
+    """8(f) rank 3: a uint8 pixel batch normalised on the device gives the same loss as the float batch the reference's
+    loaders would have produced on the host ((x/255 - mean) / std, dataloaders/rawimage_util.py)."""
+    import torch
+    from oracle import segclip_oracle as so
+    from tools.e2e_report import build_model
+    cfg = so.toy_config(use_mae=True, use_kl=True)
+    params = so.init_params(cfg, seed=31)
+    batch, noise = so.make_batch(cfg, 3, seed=32)
+    g = torch.Generator().manual_seed(33)
+    pix = torch.randint(0, 256, batch["image"].shape, generator=g, dtype=torch.uint8)
+    model = build_model(cfg, params, "fp32", "torch18_flat")
+    mean = torch.tensor(model.image_norm[0]).view(1, 1, 3, 1, 1)
+    std = torch.tensor(model.image_norm[1]).view(1, 1, 3, 1, 1)
+    batch_f = dict(batch, image=(pix.float() / 255.0 - mean) / std)
+    ref_loss, _ = so.forward(params, batch_f, noise, cfg)
+    model.inject_noise({k: v.cuda() for k, v in noise.items()})
+    ids = batch["input_ids"]
+    for img in (pix, pix.cuda()):                       # host (pinned or not) and device uint8 batches
+        loss = model(ids, torch.zeros_like(ids), batch["attention_mask"], img, image_seg=batch["image_seg"])
+        assert abs(float(loss.detach()) - float(ref_loss)) <= 1e-4 * abs(float(ref_loss))
