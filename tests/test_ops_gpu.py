@@ -69,8 +69,10 @@ def test_assignment_aggregation_fwd_bwd(empty_center):
     torch.manual_seed(3)
     B, G, Lx, D = 2, 8, 19, 64
     qf, k, v = torch.randn(B, G, D), torch.randn(B, Lx, D), torch.randn(B, Lx, D)
-    if empty_center:
-        qf[:, 5] = -50.0 * k.mean(1)              # centre 5 never wins -> count 0 -> clamp_min path
+    if empty_center:                              # centre 5 never wins -> count 0 -> clamp_min(., 1) path
+        k[..., 0] = k[..., 0].abs() + 5.0
+        qf[:, 5] = 0.0
+        qf[:, 5, 0] = -100.0
     u = torch.rand(B, G, Lx)
     extra = torch.randn(B, G, Lx) * 0.1
     d_out = torch.randn(B, G, D)
