@@ -259,7 +259,7 @@ typedef struct {
   const float* qf; /* [B,G,D] cross_ln output */
   const void* k;   /* [B,L,D] k_ln output */
   int32_t k_dtype;
-  const float* u; /* [B,G,L] torch.rand draw behind the Gumbel noise */
+  const float* u; /* [B,G,L] torch.rand draw behind the Gumbel noise; NULL = inference (plain softmax / arg-max of the logits) */
   float tau;
   const int32_t* forced_idx; /* [B,L] or NULL */
   float* logits;             /* [B,G,L] or NULL */

@@ -282,7 +282,7 @@ def grouped_conv1x1(x, w, groups):
     return torch.einsum("blgi,goi->blgo", xg, wg).reshape(b, l, c)
 
 
-def semantic_learner(x, p, pre, heads, u, kv_layout, forced_idx=None):
+def semantic_learner(x, p, pre, heads, u, kv_layout, forced_idx=None, training=True):
     """SemanticLearnerModule.forward, modules/module_seg_vit.py:277-314 (training mode).
 
     x [B,L,D]; u [B,G,L] uniform draw behind the Gumbel noise.  Returns
@@ -297,7 +297,10 @@ def semantic_learner(x, p, pre, heads, u, kv_layout, forced_idx=None):
     k = ln(grouped_conv1x1(xin, p[pre + "k_conv.weight"], heads), p, pre + "k_ln")
     v = grouped_conv1x1(xin, p[pre + "v_conv.weight"], heads)
     attn = torch.einsum("bgc,blc->bgl", q, k)
-    y = torch.softmax((attn + gumbel_from_uniform(u)) / GUMBEL_TAU, dim=1)
+    if training:
+        y = torch.softmax((attn + gumbel_from_uniform(u)) / GUMBEL_TAU, dim=1)
+    else:                                                            # module_seg_vit.py:230-231: plain softmax, no noise, no tau
+        y = torch.softmax(attn, dim=1)
     idx = y.argmax(dim=1) if forced_idx is None else forced_idx
     hard = torch.zeros_like(y).scatter_(1, idx.unsqueeze(1), 1.0)
     hard = hard - y.detach() + y                                     # :237 straight-through
@@ -342,7 +345,7 @@ def patch_embed(image, p, cfg):
     return ln(x, p, v + "ln_pre")
 
 
-def encode_image(image, p, cfg, u1, kv_layout, forced_idx=None):
+def encode_image(image, p, cfg, u1, kv_layout, forced_idx=None, training=True):
     """Main visual pass: encode_image (modules/module_clip.py:81-103) + SegViT main branch
     (modules/module_seg_vit.py:434-448).  Returns (emb [B,E], aux)."""
     v, t = "clip.visual.", "clip.visual.transformer."
@@ -350,7 +353,7 @@ def encode_image(image, p, cfg, u1, kv_layout, forced_idx=None):
     x = patch_embed(image, p, cfg)[:, 1:]                      # CLS dropped (:419)
     for i in range(cfg["first_stage_layer"]):
         x = self_attn_block(x, p, f"{t}layers0.{i}.", heads)
-    sx, hard, soft, _, idx = semantic_learner(x, p, t + "semantic_layer2.", heads, u1, kv_layout, forced_idx)
+    sx, hard, soft, _, idx = semantic_learner(x, p, t + "semantic_layer2.", heads, u1, kv_layout, forced_idx, training)
     c = sx
     for i in range(12 - cfg["first_stage_layer"]):
         c = self_attn_block(c, p, f"{t}layers2.{i}.", heads)
@@ -412,7 +415,7 @@ def mae_decoder_loss(image, hid, mask, ids_restore, p, cfg):
     return (per_patch * mk).sum() / mk.sum()
 
 
-def encode_text(ids, p, cfg):
+def encode_text(ids, p, cfg, return_hidden=False):
     """CLIP.encode_text, modules/module_clip.py:105-143 (causal mask, no padding mask)."""
     heads = cfg["text_width"] // 64
     t = ids.shape[1]
@@ -421,7 +424,8 @@ def encode_text(ids, p, cfg):
     for i in range(cfg["text_layers"]):
         x = self_attn_block(x, p, f"clip.transformer.resblocks.{i}.", heads, mask)
     hid = ln(x, p, "clip.ln_final") @ p["clip.text_projection"]
-    return hid[torch.arange(ids.shape[0]), ids.argmax(dim=-1)]
+    out = hid[torch.arange(ids.shape[0]), ids.argmax(dim=-1)]
+    return (out, hid) if return_hidden else out
 
 
 def superpixel_kl(hard, seg):
@@ -446,6 +450,14 @@ def contrastive_loss(t_loc, v_loc, t_all, v_all, logit_scale_param, rank):
     b = t_loc.shape[0]
     labels = torch.arange(b) + b * rank
     return (F.cross_entropy(t2v, labels) + F.cross_entropy(v2t, labels)) / 2.0
+
+
+def encode_image_eval(image, p, cfg, kv_layout="torch18_flat"):
+    """Inference-mode CLIP.encode_image(image, return_hidden=True) (modules/module_clip.py:89-103 with the eval branch of
+    gumbel_softmax): returns (x [B,E], hidden [B,9,E], mid_states) like the reference."""
+    x, aux = encode_image(image, p, cfg, None, kv_layout, None, training=False)
+    mid = {"hidden": aux["patches"], "attns": [{"soft_attn": aux["soft_attn"], "hard_attn": aux["hard_attn"]}]}
+    return x, aux["hidden"], mid
 
 
 def l2_normalize(x):

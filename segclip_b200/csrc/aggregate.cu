@@ -43,7 +43,8 @@ __global__ void __launch_bounds__(256) assign_fwd_kernel(sc_assign_desc a) {
   float z[G], mz = -INFINITY, ml = -INFINITY;
 #pragma unroll
   for (int g = 0; g < G; ++g) {
-    z[g] = (acc[g] + gumbel_from_uniform(a.u[((long)b * G + g) * L + l])) / a.tau;
+    // training: (logits + Gumbel) / tau; inference (u == NULL): plain logits (module_seg_vit.py:228-231)
+    z[g] = a.u ? (acc[g] + gumbel_from_uniform(a.u[((long)b * G + g) * L + l])) / a.tau : acc[g];
     mz = fmaxf(mz, z[g]);
     ml = fmaxf(ml, acc[g]);
   }
@@ -285,7 +286,7 @@ extern "C" {
 
 int sc_assign_fwd(const sc_assign_desc* a, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
-  SC_CHECK_ARG(a && a->qf && a->k && a->u && a->y_soft && a->idx && a->count, "sc_assign_fwd: null pointer");
+  SC_CHECK_ARG(a && a->qf && a->k && a->y_soft && a->idx && a->count, "sc_assign_fwd: null pointer");
   SC_CHECK_ARG(a->G == G, "sc_assign_fwd: G=%d (only 8 centres supported)", a->G);
   const size_t smem = sizeof(float) * G * a->D;
   dim3 grid(ceil_div(a->L, 8), a->B);

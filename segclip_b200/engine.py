@@ -55,6 +55,7 @@ class Plan:
         self.bufs = {}
         self.zero = []          # tensors cleared at the start of every step
         self.fwd = []
+        self.eval_tail = {"text": [], "vision": []}     # inference-only ops (hidden states of all tokens), see infer()
         self.bwd_groups = []
         self.bwd = []
 
@@ -421,7 +422,8 @@ class Engine:
             idx, count = buf(tag + ".idx", (Bn, Lx), i32), buf(tag + ".count", (Bn, G), zero=True)
             fop = ops.assign_fwd_op(qf, k, u, y_soft, idx, count, Bn, Lx, D, TAU, None, soft)
             fop_forced = ops.assign_fwd_op(qf, k, u, y_soft, idx, count, Bn, Lx, D, TAU, forced, soft)
-            pl.f((fop, fop_forced))          # tuple = (normal, teacher-forced) variant
+            fop_eval = ops.assign_fwd_op(qf, k, None, y_soft, idx, count, Bn, Lx, D, TAU, None, soft)
+            pl.f((fop, fop_forced, fop_eval))          # (training, teacher-forced, inference) variants
             agg, ssum = buf(tag + ".agg", (Mq, D)), buf(tag + ".sum", (Mq, D))
             pl.f(ops.aggregate_fwd_op(vfeat, idx, count, qf, agg, ssum, Bn, Lx, D))
             # proj_o = LN -> fc1 -> erf-GELU -> fc2 -> QuickGELU (module_seg_vit.py:271-275)
@@ -496,6 +498,9 @@ class Engine:
         st_f = ln_fwd(xe, "clip.ln_final", he, "t.ln_final")
         t_raw = buf("t.raw", (B, self.E))
         pl.f(ops.gemm_op(he, self.W("clip.text_projection"), t_raw, trans_b=True))
+        hT, hidT = buf("t.h_all", (Mt, W_), T), buf("t.hidden_all", (Mt, self.E))
+        pl.eval_tail["text"] += [ops.layernorm_op(xt, self.P("clip.ln_final.weight"), self.P("clip.ln_final.bias"), hT),
+                         ops.gemm_op(hT, self.W("clip.text_projection"), hidT, trans_b=True)]
         d_traw = buf("t.d_raw", (B, self.E))
         d_trawT, d_he, d_xe = tcopy("t.d_rawT", d_traw), sbuf("t.d_he", (B, W_), T), buf("t.d_xe", (B, W_))
         grp = sync_T(d_traw, d_trawT)
@@ -533,6 +538,13 @@ class Engine:
         st_post = ln_fwd(pooled, "clip.visual.ln_post", hpv, "v.ln_post")
         v_raw = buf("v.raw", (B, self.E))
         pl.f(ops.gemm_op(hpv, self.W("clip.visual.proj"), v_raw, trans_b=True))
+        cat9 = buf("v.cat9", (B * (G + 1), D))
+        idx_cls = (torch.arange(B, device=dev, dtype=i32) * (G + 1)).contiguous()
+        idx_ctr = (torch.arange(B * G, device=dev, dtype=i32) + torch.arange(B, device=dev, dtype=i32).repeat_interleave(G) + 1).contiguous()
+        h9, hid9 = buf("v.h9", (B * (G + 1), D), T), buf("v.hidden9", (B * (G + 1), self.E))
+        pl.eval_tail["vision"] += [ops.scatter_rows_op(pooled, idx_cls, cat9), ops.scatter_rows_op(c, idx_ctr, cat9),
+                         ops.layernorm_op(cat9, self.P("clip.visual.ln_post.weight"), self.P("clip.visual.ln_post.bias"), h9),
+                         ops.gemm_op(h9, self.W("clip.visual.proj"), hid9, trans_b=True)]
         d_vraw = buf("v.d_raw", (B, self.E))
         d_vrawT, d_hpv, d_pooled = tcopy("v.d_rawT", d_vraw), sbuf("v.d_hp", (B, D), T), buf("v.d_pooled", (B, D))
         grp = sync_T(d_vraw, d_vrawT)
@@ -771,6 +783,46 @@ class Engine:
         std = (ctypes.c_float * 3)(*norm[1])
         L.check(L.lib().sc_u8_normalize(self._u8_stage.data_ptr(), dst.data_ptr(), dst.numel(), dst.shape[-1] * dst.shape[-2],
                                         mean, std, L.stream()), "sc_u8_normalize")
+
+    def infer(self, B, ids=None, image=None, norm=None):
+        """Inference forward: no Gumbel noise, plain arg-max assignment (module_seg_vit.py:230-231),
+        no losses.  Runs the text and/or visual tower and the hidden-state tails; results are read from plan buffers."""
+        if self.params_moved():
+            raise L.SegclipB200Error("parameter storage moved after the engine was built; rebuild the engine")
+        pl = self.plan(B)
+        b = pl.bufs
+        st = L.stream()
+        if ids is not None:
+            b["in.ids"].copy_(ids, non_blocking=True)
+        if image is not None:
+            if image.dtype == torch.uint8:
+                self._upload_u8(image, b["in.image"], norm)
+            else:
+                b["in.image"].copy_(image.reshape(b["in.image"].shape).to(torch.float32), non_blocking=True)
+        self._img_event = None
+        torch._foreach_zero_(pl.zero)
+        if self.cast_op is not None:
+            self.cast_op(st)
+        for op in self.prep_ops:
+            op(st)
+        self._refresh_conv_pad()
+        # forward tape order: text tower, "wait_image", visual tower (+ head), "gather_embeddings", loss heads, MAE pass
+        section = "text"
+        for op in pl.fwd:
+            if isinstance(op, str):
+                if op == "wait_image":
+                    section = "vision"
+                elif op == "gather_embeddings":
+                    break                      # towers done: loss heads / MAE pass are training-only
+                continue
+            if (section == "text" and ids is None) or (section == "vision" and image is None):
+                continue
+            (op[2] if isinstance(op, tuple) else op)(st)
+        for which, given in (("text", ids), ("vision", image)):
+            if given is not None:
+                for op in pl.eval_tail[which]:
+                    op(st)
+        return b
 
     def backward(self, B):
         pl = self.plan(B)

@@ -184,6 +184,49 @@ def _init_tensor(shape, init, cfg):
 # ----------------------------------------------------------------------------------------------
 # autograd bridge
 # ----------------------------------------------------------------------------------------------
+class _ClipFacade(_Node):
+    """`model.clip`: owns the CLIP parameters (reference attribute tree) and exposes the inference entry points of
+    modules/module_clip.py:89-143.  Training-mode encoding is part of the fused SegCLIP.forward()."""
+
+    def _own(self):
+        return self.__dict__["_owner"]()
+
+    def encode_image(self, image, return_hidden=False, video_frame=-1, mask_ratio=0.):
+        owner = self._own()
+        if owner.training or mask_ratio > 0.:
+            raise NotImplementedError("training-mode / masked encode_image is fused into SegCLIP.forward(); call model(...)")
+        eng = owner._get_engine()
+        image = torch.as_tensor(image)
+        B = image.shape[0]
+        if image.shape[-1] != eng.patch * eng.grid:
+            raise NotImplementedError("bicubic positional-embedding resize (module_clip_vtransformer.py:35-53) is not built: "
+                                      "inputs must be %dx%d" % (eng.patch * eng.grid, eng.patch * eng.grid))
+        b = eng.infer(B, image=image.to(eng.dev), norm=owner.image_norm)
+        hidden = b["v.hidden9"].view(B, G + 1, eng.E).clone()
+        x = hidden[:, 0]
+        if not return_hidden:
+            return x
+        patches = b["v%d.x_out" % (eng.fsl - 1)] if eng.fsl > 0 else b["v.stem.x0"]
+        idx = b["v.sem.idx"].long()
+        hard = torch.zeros(B, G, eng.Lp, device=eng.dev).scatter_(1, idx.unsqueeze(1), 1.0)
+        mid = {"hidden": patches.view(B, eng.Lp, eng.vw).clone(),
+               "attns": [{"soft_attn": b["v.sem.soft"].clone(), "hard_attn": hard}]}
+        return x, hidden, mid
+
+    def encode_text(self, text, attn_mask=None, return_hidden=False, mask_ratio=0.):
+        owner = self._own()
+        if owner.training or mask_ratio > 0.:
+            raise NotImplementedError("training-mode / masked encode_text is fused into SegCLIP.forward(); call model(...)")
+        eng = owner._get_engine()
+        text = torch.as_tensor(text)
+        B = text.shape[0]
+        b = eng.infer(B, ids=text.to(eng.dev))
+        x = b["t.raw"].clone()
+        if return_hidden:
+            return x, b["t.hidden_all"].view(B, eng.Tctx, eng.E).clone()
+        return x
+
+
 class _NativeStep(torch.autograd.Function):
     """loss = native_forward(params...); backward replays the native backward tape."""
 
@@ -240,6 +283,9 @@ class SegCLIP(nn.Module):
         self.use_text_mae_recon = False
         self.vis_mask_ratio = get_attr(task_config, "mae_vis_mask_ratio", 0.75)
         assert abs(self.vis_mask_ratio - 0.75) < 1e-9, "only mae_vis_mask_ratio=0.75 (reference default) is built"
+        import weakref
+        self.add_module("clip", _ClipFacade())
+        self.clip.__dict__["_owner"] = weakref.ref(self)
         for name, shape, init in _param_specs(self.cfg):
             p = nn.Parameter(_init_tensor(shape, init, self.cfg))
             if name in FROZEN_STEM:
@@ -374,6 +420,55 @@ class SegCLIP(nn.Module):
         inputs = dict(ids=ids, image=img, seg=seg, norm=self.image_norm)
         params = [p for _, p in self._active_items]
         return _NativeStep.apply(self, b, inputs, noise, self._forced, *params)
+
+    # ---- inference-mode getters (modules/modeling.py:258-372) ---------------------------------------
+    def get_sequence_output(self, input_ids, token_type_ids, attention_mask, shaped=False, return_hidden=False, seq_model=None,
+                            mask_ratio=0.):
+        ids = torch.as_tensor(input_ids)
+        ids = ids.view(-1, ids.shape[-1])
+        bs = ids.size(0)
+        out = self.clip.encode_text(ids, return_hidden=return_hidden, mask_ratio=mask_ratio)
+        if isinstance(out, tuple):
+            return tuple(t.float().view(bs, -1, t.size(-1)) for t in out)
+        return out.float().view(bs, -1, out.size(-1))
+
+    def get_visual_output(self, image, shaped=False, image_frame=-1, return_hidden=False, vis_model=None, mask_ratio=0.):
+        image = torch.as_tensor(image)
+        if shaped is False:
+            b, pair, channel, h, w = image.shape
+            image = image[:, 0].reshape(b, channel, h, w)
+        bs = image.size(0)
+        out = self.clip.encode_image(image, return_hidden=return_hidden, mask_ratio=mask_ratio)
+        if isinstance(out, tuple):
+            return tuple([t.float().view(bs, -1, t.size(-1)) for t in out[:2]] + [out[2]])
+        return out.float().view(bs, -1, out.size(-1))
+
+    def get_sequence_visual_output(self, input_ids, token_type_ids, attention_mask, image, shaped=False, image_frame=-1,
+                                   return_hidden=False, seq_model=None, vis_model=None):
+        seq = self.get_sequence_output(input_ids, token_type_ids, attention_mask, shaped=shaped, return_hidden=return_hidden)
+        vis = self.get_visual_output(image, shaped=shaped, image_frame=image_frame, return_hidden=return_hidden)
+        return seq, vis
+
+    def _loose_similarity(self, sequence_output, visual_output, logit_scale=None):
+        """Inference branch of modules/modeling.py:338-362: cosine logits scaled by min(exp(logit_scale), 100)."""
+        if self.training:
+            raise NotImplementedError("the training-mode similarity (all-gather InfoNCE) is fused into SegCLIP.forward()")
+        dev = self._get_engine().dev
+        t = sequence_output.squeeze(1).contiguous().float().to(dev)
+        v = visual_output.squeeze(1).contiguous().float().to(dev)
+        tn, vn = torch.empty_like(t), torch.empty_like(v)
+        ti, vi = torch.empty(t.shape[0], device=dev), torch.empty(v.shape[0], device=dev)
+        ops.l2norm_fwd_op(t, tn, ti)()
+        ops.l2norm_fwd_op(v, vn, vi)()
+        p = self.clip.logit_scale if logit_scale is None else logit_scale
+        scale = min(math.exp(float(p)), 100.0)
+        t2v = torch.empty(t.shape[0], v.shape[0], device=dev)
+        ops.gemm_op(tn, vn, t2v, alpha=scale)()
+        return t2v, t2v.T
+
+    def get_similarity_logits(self, sequence_output, visual_output, attention_mask, shaped=False):
+        t2v, v2t = self._loose_similarity(sequence_output, visual_output)
+        return t2v, v2t, ()
 
     # ---- introspection used by tests -----------------------------------------------------------
     def debug_buffers(self, B):

@@ -239,7 +239,7 @@ def mean_cat_bwd_op(dout, dx, B, n, D):
 def assign_fwd_op(qf, k, u, y_soft, idx, count, B, Lp, D, tau=0.9, forced_idx=None, soft=None, logits=None):
     a = L.AssignDesc()
     a.B, a.G, a.L, a.D = B, 8, Lp, D
-    a.qf, a.k, a.k_dtype, a.u, a.tau = qf.data_ptr(), k.data_ptr(), L.dt(k), u.data_ptr(), tau
+    a.qf, a.k, a.k_dtype, a.u, a.tau = qf.data_ptr(), k.data_ptr(), L.dt(k), _p(u), tau
     a.forced_idx, a.logits, a.soft = _p(forced_idx), _p(logits), _p(soft)
     a.y_soft, a.idx, a.count = y_soft.data_ptr(), idx.data_ptr(), count.data_ptr()
     return Op("sc_assign_fwd", (C.byref(a),), (a, qf, k, u, y_soft, idx, count, forced_idx, soft, logits))

@@ -152,3 +152,38 @@ def test_uint8_image_boundary_matches_host_normalisation():
     for img in (pix, pix.cuda()):                       # host (pinned or not) and device uint8 batches
         loss = model(ids, torch.zeros_like(ids), batch["attention_mask"], img, image_seg=batch["image_seg"])
         assert abs(float(loss.detach()) - float(ref_loss)) <= 1e-4 * abs(float(ref_loss))
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_inference_path_matches_oracle(precision):
+    """8(f) rank 4: eval-mode encode_image / encode_text / getters / similarity logits against the oracle's eval functions
+    (which are pinned to the reference's eval mode in tests/test_oracle_vs_reference.py)."""
+    import torch
+    from oracle import segclip_oracle as so
+    from tools.e2e_report import build_model
+    cfg = so.toy_config(use_mae=True, use_kl=True)
+    params = so.init_params(cfg, seed=41)
+    batch, _ = so.make_batch(cfg, 3, seed=42)
+    img, ids = batch["image"][:, 0], batch["input_ids"][:, 0]
+    ox, ohid, omid = so.encode_image_eval(img, params, cfg)
+    otx, othid = so.encode_text(ids, params, cfg, return_hidden=True)
+    model = build_model(cfg, params, precision, "torch18_flat").eval()
+    with torch.no_grad():
+        x, hid, mid = model.clip.encode_image(img, return_hidden=True)
+        tx, thid = model.clip.encode_text(ids, return_hidden=True)
+        seq, vis = model.get_sequence_visual_output(batch["input_ids"], None, None, batch["image"])
+        t2v, v2t, _ = model.get_similarity_logits(seq, vis, None)
+    tol = 1e-4 if precision == "fp32" else 3e-2
+
+    def rel(a, b):
+        return float((a.float().cpu() - b).abs().max() / (b.abs().max() + 1e-9))
+    assert rel(x, ox) < tol and rel(hid, ohid) < tol and rel(tx, otx) < tol and rel(thid, othid) < tol
+    assert rel(mid["hidden"], omid["hidden"]) < tol
+    assert rel(mid["attns"][0]["soft_attn"], omid["attns"][0]["soft_attn"]) < (1e-4 if precision == "fp32" else 0.1)
+    flips = float((mid["attns"][0]["hard_attn"].cpu() != omid["attns"][0]["hard_attn"].detach()).float().mean())
+    assert flips == 0.0 if precision == "fp32" else flips < 0.05
+    assert seq.shape == (3, 1, cfg["embed_dim"]) and vis.shape == (3, 1, cfg["embed_dim"])
+    scale = min(float(params["clip.logit_scale"].exp()), 100.0)
+    ref = scale * so.l2_normalize(otx) @ so.l2_normalize(ox).t()
+    assert rel(t2v, ref) < tol and torch.equal(v2t, t2v.T)
+    assert model(batch["input_ids"], None, None, batch["image"]) is None          # eval forward() returns None (modeling.py:254-256)

@@ -38,3 +38,25 @@ def test_toy_loss_and_grads_match_reference(kv_layout, heads_on):
     for name, g in grads.items():
         if name not in ref_grads:
             assert float(g.abs().max()) == 0.0, name
+
+
+def test_eval_mode_encoders_match_reference():
+    """Inference path: eval-mode encode_image / encode_text of the reference (plain softmax assignment,
+    modules/module_seg_vit.py:230-231) against the oracle's eval functions."""
+    cfg = so.toy_config()
+    model = rh.build_reference_model(cfg)
+    params = so.init_params(cfg, seed=41)
+    model.load_state_dict(params, strict=False)
+    model.eval()
+    batch, _ = so.make_batch(cfg, 3, seed=42)
+    img, ids = batch["image"][:, 0], batch["input_ids"][:, 0]
+    with torch.no_grad():
+        x, hid, mid = model.clip.encode_image(img, return_hidden=True)
+        tx, thid = model.clip.encode_text(ids, return_hidden=True)
+        ox, ohid, omid = so.encode_image_eval(img, params, cfg)
+        otx, othid = so.encode_text(ids, params, cfg, return_hidden=True)
+    model.train()
+    for a, b in ((x, ox), (hid, ohid), (mid["hidden"], omid["hidden"]), (tx, otx), (thid, othid),
+                 (mid["attns"][0]["soft_attn"], omid["attns"][0]["soft_attn"]),
+                 (mid["attns"][0]["hard_attn"], omid["attns"][0]["hard_attn"])):
+        assert float((a - b).abs().max()) < 1e-5
