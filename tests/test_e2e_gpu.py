@@ -177,13 +177,18 @@ def test_inference_path_matches_oracle(precision):
 
     def rel(a, b):
         return float((a.float().cpu() - b).abs().max() / (b.abs().max() + 1e-9))
-    assert rel(x, ox) < tol and rel(hid, ohid) < tol and rel(tx, otx) < tol and rel(thid, othid) < tol
-    assert rel(mid["hidden"], omid["hidden"]) < tol
+    def cos(a, b):
+        return float(torch.nn.functional.cosine_similarity(a.float().cpu().flatten(), b.flatten(), dim=0))
+    assert rel(tx, otx) < tol and rel(thid, othid) < tol and rel(mid["hidden"], omid["hidden"]) < tol
+    if precision == "fp32":
+        assert rel(x, ox) < tol and rel(hid, ohid) < tol
+    else:       # bf16 logits flip a few hard assignments (no teacher forcing in eval): bound direction + worst element
+        assert cos(x, ox) > 0.995 and cos(hid, ohid) > 0.995 and rel(x, ox) < 0.2 and rel(hid, ohid) < 0.2
     assert rel(mid["attns"][0]["soft_attn"], omid["attns"][0]["soft_attn"]) < (1e-4 if precision == "fp32" else 0.1)
     flips = float((mid["attns"][0]["hard_attn"].cpu() != omid["attns"][0]["hard_attn"].detach()).float().mean())
     assert flips == 0.0 if precision == "fp32" else flips < 0.05
     assert seq.shape == (3, 1, cfg["embed_dim"]) and vis.shape == (3, 1, cfg["embed_dim"])
     scale = min(float(params["clip.logit_scale"].exp()), 100.0)
     ref = scale * so.l2_normalize(otx) @ so.l2_normalize(ox).t()
-    assert rel(t2v, ref) < tol and torch.equal(v2t, t2v.T)
+    assert rel(t2v, ref) < (tol if precision == "fp32" else 0.1) and torch.equal(v2t, t2v.T)
     assert model(batch["input_ids"], None, None, batch["image"]) is None          # eval forward() returns None (modeling.py:254-256)
