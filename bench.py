@@ -96,7 +96,7 @@ def run_reference(args):
     from oracle import segclip_oracle as so
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    cfg = model_config(so, args)
+    cfg = model_config(args)
     Bc = args.cpu_batch
     params = so.init_params(cfg, seed=0)
     frozen = ("vis_mae_decoder.decoder_pos_embed",)
@@ -120,11 +120,11 @@ def run_reference(args):
         "e2e": {"value": v, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
 
 
-def model_config(so, args):
+def model_config(args):
+    from segclip_b200 import config
     if args.model == "vitl14":      # BASELINE configs[4]: width 1024 / 16 heads / patch 14, text 768 / 12 heads, E = 768 (F5: 10+2 layers)
-        return so.vit_b16_config(vision_width=1024, text_width=768, embed_dim=768, patch=14, grid=16, use_mae=args.heads,
-                                 use_kl=args.heads)
-    return so.vit_b16_config(use_mae=args.heads, use_kl=args.heads)
+        return config.vit_l14(use_mae=args.heads, use_kl=args.heads)
+    return config.vit_b16(use_mae=args.heads, use_kl=args.heads)
 
 
 def workload_name(args):
@@ -154,9 +154,8 @@ def main():
         return run_reference(args)
 
     import torch.distributed as dist
-    from oracle.ref_harness import fake_clip_state_dict          # shapes only (test/bench infrastructure)
-    from oracle import segclip_oracle as so
     from segclip_b200 import _lib
+    from segclip_b200.config import shape_state_dict
     from segclip_b200.modeling import SegCLIP
 
     rank = int(os.environ.get("RANK", "0"))
@@ -168,11 +167,11 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
-    cfg = model_config(so, args)
+    cfg = model_config(args)
     tc = argparse.Namespace(local_rank=local, rank=rank, world_size=world, first_stage_layer=10,
                             use_vision_mae_recon=args.heads, use_seglabel=args.heads, precision=args.precision)
     torch.manual_seed(0)
-    model = SegCLIP(fake_clip_state_dict(cfg), tc).to(dev).train()
+    model = SegCLIP(shape_state_dict(cfg), tc).to(dev).train()
     net = model
     if world > 1:
         from segclip_b200.p2p import EmbeddingExchange
@@ -251,16 +250,18 @@ def main():
                      "launches_per_step": gemm["launches"], "share_of_step": gemm["ms"] / ms, "peak_source": pk["src"]},
     }
     if world == 1 and not args.no_cpu_baseline:
-        out["cpu_baseline"] = cpu_baseline(so, args)
+        out["cpu_baseline"] = cpu_baseline(args)
     print(json.dumps(out))
     if world > 1:
         dist.barrier()
 
 
-def cpu_baseline(so, args):
+def cpu_baseline(args):
+    """The only leg of the own arm that touches oracle/: the CPU port timed beside the GPU number."""
+    from oracle import segclip_oracle as so
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    cfg = model_config(so, args)
+    cfg = model_config(args)
     Bc = args.cpu_batch
     params = so.init_params(cfg, seed=0)
     batch, noise = so.make_batch(cfg, Bc, seed=0)

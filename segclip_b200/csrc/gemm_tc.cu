@@ -43,8 +43,9 @@ struct MapKey {
   const void* ptr;
   uint64_t d0, d1, stride;
   uint32_t b0, b1;
+  int swizzle;
   bool operator==(const MapKey& o) const {
-    return ptr == o.ptr && d0 == o.d0 && d1 == o.d1 && stride == o.stride && b0 == o.b0 && b1 == o.b1;
+    return ptr == o.ptr && d0 == o.d0 && d1 == o.d1 && stride == o.stride && b0 == o.b0 && b1 == o.b1 && swizzle == o.swizzle;
   }
 };
 struct MapKeyHash {
@@ -54,16 +55,23 @@ struct MapKeyHash {
     h = h * 1000003u ^ k.d1;
     h = h * 1000003u ^ k.stride;
     h = h * 1000003u ^ ((uint64_t)k.b0 << 32 | k.b1);
+    h = h * 1000003u ^ (uint64_t)k.swizzle;
     return h;
   }
 };
 
 // bf16 2-D tensor map, 128B swizzle, zero fill.  dim0 is the contiguous dimension.
 int sc_get_tensor_map(const void* ptr, uint64_t dim0, uint64_t dim1, uint64_t stride_elems, uint32_t box0, uint32_t box1,
-                   CUtensorMap* out) {
+                      CUtensorMap* out) {
+  return sc_get_tensor_map_sw(ptr, dim0, dim1, stride_elems, box0, box1, 128, out);
+}
+
+// same with an explicit swizzle span in bytes (128 or 64; 64 is used by the TMA-store epilogue's 32 x 32 bf16 boxes)
+int sc_get_tensor_map_sw(const void* ptr, uint64_t dim0, uint64_t dim1, uint64_t stride_elems, uint32_t box0, uint32_t box1,
+                         int swizzle_bytes, CUtensorMap* out) {
   static std::mutex mu;
   static std::unordered_map<MapKey, CUtensorMap, MapKeyHash> cache;
-  MapKey key{ptr, dim0, dim1, stride_elems, box0, box1};
+  MapKey key{ptr, dim0, dim1, stride_elems, box0, box1, swizzle_bytes};
   {
     std::lock_guard<std::mutex> g(mu);
     auto it = cache.find(key);
@@ -82,7 +90,8 @@ int sc_get_tensor_map(const void* ptr, uint64_t dim0, uint64_t dim1, uint64_t st
   cuuint32_t box[2] = {box0, box1};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), gdim, gstride, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     sc_set_error("cuTensorMapEncodeTiled failed (%d): ptr=%p dims=(%llu,%llu) stride=%llu box=(%u,%u)", (int)r, ptr,

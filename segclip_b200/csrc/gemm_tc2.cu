@@ -7,18 +7,28 @@
 //   full[stage]  (leader's): both CTAs' TMA loads complete_tx on the leader's barrier (peer bit cleared)
 //   empty[stage] (both)    : tcgen05.commit ... multicast::cluster 0b11 from the leader's MMA thread
 //   tmem_full[acc] (both)  : same multicast commit after the last k-block
-//   tmem_empty[acc] (leader's, 16 arrivals): epilogue warps of both CTAs arrive through the cluster window
+//   tmem_empty[acc] (leader's, 2 x EPI2_WARPS arrivals): epilogue warps of both CTAs arrive through the cluster window
 // Everything else (operand layouts, split-K, fused epilogues) is identical to gemm_tc.cu.
 #include "gemm_tc_common.cuh"
 
 namespace {
 using namespace tc;
 
-constexpr int STAGES2 = 6;
+#ifndef SC_TC2_EPI_WARPS
+#define SC_TC2_EPI_WARPS 8
+#endif
+// 8 epilogue warps (4 TMEM lane quarters x 2 column halves); 16 were measured on B200 and change nothing: the epilogue is
+// bound by L1TEX data-pipe wavefronts, not by latency (see epi_finish_tma).  Each warp owns 8 KB of staging (four 2 KB TMA
+// boxes, or one 4 KB fp32 transpose patch), which costs one stage of the operand ring (5 x 32 KB).
+constexpr int EPI2_WARPS = SC_TC2_EPI_WARPS;
+constexpr int EPI2_COLS = 256 / (EPI2_WARPS / 4);      // accumulator columns per warp
+constexpr int THREADS2 = (EPI2_WARPS + 2) * 32;
+constexpr int STAGES2 = 5;
+constexpr int EPI2_STAGE_BYTES = 8192;   // per epilogue warp
 constexpr int A2_BYTES = 128 * BK * 2;
 constexpr int B2_BYTES = 128 * BK * 2;
 constexpr int STAGE2_BYTES = A2_BYTES + B2_BYTES;
-constexpr int SMEM2_BYTES = STAGES2 * STAGE2_BYTES + 256 + NUM_EPI_WARPS * 4096;
+constexpr int SMEM2_BYTES = STAGES2 * STAGE2_BYTES + EPI2_WARPS * EPI2_STAGE_BYTES + 256;
 constexpr uint32_t PEER_MASK = 0xFEFFFFFFu;   // clears the CTA-rank bit of a shared::cluster address -> CTA 0 of the pair
 
 SC_DEVINL uint32_t cluster_ctarank() {
@@ -53,20 +63,21 @@ SC_DEVINL void mbar_arrive_leader(uint64_t* bar) {
 }
 
 template <bool A_MN, bool B_MN, int EF>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
-gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int tiles_m, int tiles_n,
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS2, 1)
+gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmC2, int tiles_m, int tiles_n,
                 int splits, int kb_total, int kb_per_split, EpiParams ep) {
   extern __shared__ __align__(1024) uint8_t smem[];
   if ((smem_u32(smem) & 1023u) != 0u) __trap();
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + STAGES2 * A2_BYTES;
-  uint64_t* bars = (uint64_t*)(smem + STAGES2 * STAGE2_BYTES);
+  uint8_t* epi_stage = smem + STAGES2 * STAGE2_BYTES;                       // 1024-byte aligned (swizzled TMA boxes)
+  uint64_t* bars = (uint64_t*)(epi_stage + EPI2_WARPS * EPI2_STAGE_BYTES);
   uint64_t* full_bar = bars;
   uint64_t* empty_bar = bars + STAGES2;
   uint64_t* tmem_full = bars + 2 * STAGES2;
   uint64_t* tmem_empty = tmem_full + 2;
   uint32_t* tmem_slot = (uint32_t*)(tmem_empty + 2);
-  uint8_t* epi_stage = smem + STAGES2 * STAGE2_BYTES + 256;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -80,12 +91,12 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tmem_full[i], 1);
-      mbar_init(&tmem_empty[i], 2 * NUM_EPI_WARPS);
+      mbar_init(&tmem_empty[i], 2 * EPI2_WARPS);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
-  if (warp == NUM_EPI_WARPS + 1) {
+  if (warp == EPI2_WARPS + 1) {
     asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u)
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
@@ -96,7 +107,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   const uint32_t tmem_base = *tmem_slot;
   const int num_items = tiles_m * tiles_n * splits;
 
-  if (warp == NUM_EPI_WARPS) {
+  if (warp == EPI2_WARPS) {
     // =============================== TMA producer (both CTAs) ===============================
     if (lane == 0) {
       asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tmA) : "memory");
@@ -110,6 +121,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         const int m0 = mt * 256 + rank * 128, n0 = nt * 256 + rank * 128;
         const int kb0 = sp * kb_per_split;
         const int kb1 = min(kb_total, kb0 + kb_per_split);
+        // (prefetching the next tile's operands into L2 from here was measured on B200: -15 % on the K = 768 shapes)
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           if (rank == 0) mbar_expect_tx(&full_bar[stage], 2 * STAGE2_BYTES);
@@ -131,7 +143,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         }
       }
     }
-  } else if (warp == NUM_EPI_WARPS + 1) {
+  } else if (warp == EPI2_WARPS + 1) {
     // =============================== MMA issuer (leader CTA only) ===============================
     if (lane == 0 && rank == 0) {
       constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((A_MN ? 1u : 0u) << 15) | ((B_MN ? 1u : 0u) << 16) |
@@ -168,28 +180,38 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   } else {
     // =============================== epilogue (both CTAs, own 128 rows) ===============================
     const int quarter = warp & 3;
-    const int half = warp >> 2;
-    const uint32_t stage = smem_u32(epi_stage) + warp * 4096;
+    const int cgrp = warp >> 2;
+    const uint32_t stage = smem_u32(epi_stage) + warp * EPI2_STAGE_BYTES;
+    uint32_t g = 0;
     const int l7 = lane & 7, l3 = lane >> 3;
     int it = 0;
     for (int item = pair; item < num_items; item += npairs, ++it) {
       const int nt = item % tiles_n;
       const int mt = (item / tiles_n) % tiles_m;
-      const int nbase = nt * 256 + half * 128;
+      const int nbase = nt * 256 + cgrp * EPI2_COLS;
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
+      float4 breg = make_float4(0.f, 0.f, 0.f, 0.f);
+      if constexpr (EpiTma<EF>::value && (EF & EF_BIAS) != 0) {
+        if (nbase + 4 * lane < ep.N) breg = __ldg((const float4*)(ep.bias + nbase + 4 * lane));
+      }
       mbar_wait(&tmem_full[acc], acc_phase);
       tcgen05_fence_after();
-      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * 256 + half * 128;
+      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * 256 + cgrp * EPI2_COLS;
       const int mrow0 = mt * 256 + rank * 128 + quarter * 32;
 #pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
+      for (int c = 0; c < EPI2_COLS / 32; ++c) {
         float v[32];
-        float4 b4, pre[8];
         const int n0 = nbase + c * 32;
-        epi_prefetch<EF>(ep, lane, mrow0, n0, b4, pre);     // global reads first: latency overlaps the TMEM load
-        tmem_ld32(taddr + c * 32, v);
-        epi_finish<EF>(ep, v, stage, lane, mrow0, n0, b4, pre);
+        if constexpr (EpiTma<EF>::value) {
+          tmem_ld32(taddr + c * 32, v);
+          epi_finish_tma<EF>(ep, v, stage, lane, mrow0, n0, g++, c, breg, &tmC, &tmC2);
+        } else {
+          float4 b4, pre[8];
+          epi_prefetch<EF>(ep, lane, mrow0, n0, b4, pre);     // global reads first: latency overlaps the TMEM load
+          tmem_ld32(taddr + c * 32, v);
+          epi_finish<EF>(ep, v, stage, lane, mrow0, n0, b4, pre);
+        }
       }
       tcgen05_fence_before();
       __syncwarp();
@@ -197,9 +219,12 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     }
   }
 
+  if constexpr (EpiTma<EF>::value) {
+    if (warp < EPI2_WARPS && lane == 0) bulk_wait_all();     // staging smem must outlive the last TMA stores
+  }
   tcgen05_fence_before();
   cluster_sync_all();
-  if (warp == NUM_EPI_WARPS + 1) {
+  if (warp == EPI2_WARPS + 1) {
     tcgen05_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
   }
@@ -207,6 +232,14 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 
 template <bool A_MN, bool B_MN, int EF>
 int launch2(const sc_gemm_desc* d, const CUtensorMap& ta, const CUtensorMap& tb, int splits, cudaStream_t st) {
+  CUtensorMap tc_ = ta, tc2_ = ta;          // placeholders for the kinds that do not store through the TMA
+  if constexpr (EpiTma<EF>::value) {
+    int rc;
+    if ((rc = sc_get_tensor_map_sw(d->C, d->N, d->M, d->ldc, 32, 32, 64, &tc_))) return rc;
+    if constexpr (EpiTma<EF>::two) {
+      if ((rc = sc_get_tensor_map_sw(d->C2, d->N, d->M, d->ldc, 32, 32, 64, &tc2_))) return rc;
+    }
+  }
   auto kern = gemm_tc2_kernel<A_MN, B_MN, EF>;
   static bool configured = false;
   if (!configured) {
@@ -223,7 +256,7 @@ int launch2(const sc_gemm_desc* d, const CUtensorMap& ta, const CUtensorMap& tb,
   const int items = tiles_m * tiles_n * splits;
   const int max_pairs = sc_num_sms() / 2;
   const int pairs = items < max_pairs ? items : max_pairs;
-  kern<<<2 * pairs, NUM_THREADS, SMEM2_BYTES, st>>>(ta, tb, tiles_m, tiles_n, splits, kb_total, kb_per, ep);
+  kern<<<2 * pairs, THREADS2, SMEM2_BYTES, st>>>(ta, tb, tc_, tc2_, tiles_m, tiles_n, splits, kb_total, kb_per, ep);
   SC_LAUNCH_CHECK();
   return SC_OK;
 }

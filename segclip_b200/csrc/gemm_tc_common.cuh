@@ -328,6 +328,78 @@ SC_DEVINL void epi_finish(const EpiParams& ep, float (&v)[32], uint32_t stage, i
   }
 }
 
+// ---- TMA-store flavour of the bf16 epilogue (2-CTA kernel) --------------------------------------------------------
+// ncu on the c_fc forward showed the L1TEX data pipe -- shared by UMMA operand fetch, LDS/STS and global LD/ST
+// wavefronts -- 100 % busy: per 128 x 256 CTA tile 3072 (UMMA) + 3684 (smem transpose) + 1273 (global) wavefronts against
+// 6144 cycles of MMA.  Here the row-per-thread values are packed to bf16, written once into a 32 x 32 box in the
+// SWIZZLE_64B layout (conflict-free 16-byte stores) and handed to the TMA (cp.async.bulk.tensor store): no transposed
+// read-back, no per-lane global stores.  Four 2 KB boxes per warp rotate; a box is rewritten only after the bulk group
+// that read it has completed (cp.async.bulk.wait_group.read).
+SC_DEVINL void tma_store_2d(const CUtensorMap* map, uint32_t src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+               ::"l"((uint64_t)map), "r"(src), "r"(c0), "r"(c1) : "memory");
+}
+SC_DEVINL void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+SC_DEVINL void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+SC_DEVINL void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
+template <int EF>
+struct EpiTma {
+  static constexpr bool value = EpiKind<EF>::bf16_path && !EpiKind<EF>::aux;
+  static constexpr bool two = value && (EF & EF_C2) != 0;
+};
+
+// one warp, one chunk of 32 rows x 32 accumulator columns; `g` = running chunk counter of the warp (buffer rotation)
+template <int EF>
+SC_DEVINL void epi_finish_tma(const EpiParams& ep, float (&v)[32], uint32_t stage, int lane, int mrow0, int n0, uint32_t g,
+                              int c, const float4& breg, const CUtensorMap* tmC, const CUtensorMap* tmC2) {
+  constexpr bool two = EpiTma<EF>::two;
+  const uint32_t buf_out = stage + ((two ? 2 * g + 1 : g) & 3u) * 2048u;
+  const uint32_t buf_c2 = stage + ((2 * g) & 3u) * 2048u;
+  if (lane == 0) bulk_wait_read<two ? 1 : 3>();      // the group that last read these boxes has retired
+  if constexpr ((EF & EF_BIAS) != 0) {
+    // breg = the 4 bias values of columns 4*lane.. of this warp's 128-column range, loaded once per tile BEFORE the wait
+    // for the accumulator (the L1 left beside 224 KB of smem is ~4 KB: a per-chunk __ldg exposed an L2 round trip per chunk
+    // -- the top stall of the old epilogue in the ncu source view)
+    const int src = c * 8;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      v[4 * j] += __shfl_sync(0xffffffffu, breg.x, src + j);
+      v[4 * j + 1] += __shfl_sync(0xffffffffu, breg.y, src + j);
+      v[4 * j + 2] += __shfl_sync(0xffffffffu, breg.z, src + j);
+      v[4 * j + 3] += __shfl_sync(0xffffffffu, breg.w, src + j);
+    }
+  }
+  const int sw = (lane >> 1) & 3;
+  __syncwarp();
+  if constexpr (two) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      sts128b(buf_c2 + lane * 64 + ((j ^ sw) << 4), make_uint4(pack2_bf16(v[8 * j], v[8 * j + 1]), pack2_bf16(v[8 * j + 2], v[8 * j + 3]),
+                                                                pack2_bf16(v[8 * j + 4], v[8 * j + 5]), pack2_bf16(v[8 * j + 6], v[8 * j + 7])));
+  }
+  if constexpr ((EF & EF_QGELU) != 0) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = qgelu_fast(v[j]);
+  }
+  if constexpr ((EF & EF_GELU) != 0) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = act_fwd(v[j], SC_ACT_GELU_ERF);
+  }
+#pragma unroll
+  for (int j = 0; j < 4; ++j)
+    sts128b(buf_out + lane * 64 + ((j ^ sw) << 4), make_uint4(pack2_bf16(v[8 * j], v[8 * j + 1]), pack2_bf16(v[8 * j + 2], v[8 * j + 3]),
+                                                               pack2_bf16(v[8 * j + 4], v[8 * j + 5]), pack2_bf16(v[8 * j + 6], v[8 * j + 7])));
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic-proxy writes -> visible to the TMA
+  __syncwarp();
+  if (lane == 0 && n0 < ep.N && mrow0 < ep.M) {
+    if constexpr (two) tma_store_2d(tmC2, buf_c2, n0, mrow0);
+    tma_store_2d(tmC, buf_out, n0, mrow0);
+  }
+  if (lane == 0) bulk_commit();
+}
+
 // Shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout), SWIZZLE_128B.
 //   K-major : rows of 128 B, 8-row swizzle atoms 1024 B apart (SBO); LBO unused (1).
 //   MN-major: 64-element (128 B) MN chunks; k rows 128 B apart, 8-k-row atoms SBO=1024 B apart,
@@ -349,4 +421,6 @@ SC_DEVINL uint64_t make_smem_desc(uint32_t smem_addr) {
 // host helpers (gemm_tc.cu)
 int sc_get_tensor_map(const void* ptr, uint64_t dim0, uint64_t dim1, uint64_t stride_elems, uint32_t box0, uint32_t box1,
                       CUtensorMap* out);
+int sc_get_tensor_map_sw(const void* ptr, uint64_t dim0, uint64_t dim1, uint64_t stride_elems, uint32_t box0, uint32_t box1,
+                         int swizzle_bytes, CUtensorMap* out);
 int sc_select_epilogue(const sc_gemm_desc* d, int splits);

@@ -19,13 +19,19 @@ SHAPES = [  # name, M, N, K, ta, tb, kwargs
     ("c_proj wgrad", 768, 3072, 50176, True, True, dict(acc=True, out=torch.float32)),
     ("qkv    wgrad", 2304, 768, 50176, True, True, dict(acc=True, out=torch.float32)),
     ("text qkv fwd", 19712, 1536, 512, False, False, dict(bias=True, out=torch.bfloat16)),
+    ("text c_fc fwd", 19712, 2048, 512, False, False, dict(bias=True, act=1, c2=True, out=torch.bfloat16)),
+    ("text c_proj dgrad*", 19712, 2048, 512, False, True, dict(out=torch.bfloat16, aux=True)),
+    ("text c_proj fwd", 19712, 512, 2048, False, False, dict(bias=True, residual=True, out=torch.float32)),
     ("plain 8192^3", 8192, 8192, 8192, False, False, dict(out=torch.bfloat16)),
 ]
 
 
 def main():
     dev = "cuda"
+    only = sys.argv[1] if len(sys.argv) > 1 else None       # substring filter (ncu captures of one shape)
     for name, M, N, K, ta, tb, kw in SHAPES:
+        if only and only not in name:
+            continue
         A = torch.randn((K, M) if ta else (M, K), device=dev).bfloat16()
         B = torch.randn((K, N) if tb else (N, K), device=dev).bfloat16()
         C = torch.zeros(M, N, device=dev, dtype=kw["out"])
@@ -47,7 +53,7 @@ def main():
         e1.record()
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / n
-        print("%-14s M=%6d N=%5d K=%6d  %8.3f ms  %7.1f TFLOP/s" % (name, M, N, K, ms, 2.0 * M * N * K / ms / 1e9))
+        print("%-18s M=%6d N=%5d K=%6d  %8.3f ms  %7.1f TFLOP/s" % (name, M, N, K, ms, 2.0 * M * N * K / ms / 1e9))
 
 
 if __name__ == "__main__":

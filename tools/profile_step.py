@@ -14,8 +14,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
 from bench import synthetic_batch                      # noqa: E402
-from oracle.ref_harness import fake_clip_state_dict    # noqa: E402
-from oracle import segclip_oracle as so                # noqa: E402
+from segclip_b200 import config                        # noqa: E402
 from segclip_b200 import _lib as L                     # noqa: E402
 from segclip_b200.modeling import SegCLIP              # noqa: E402
 
@@ -44,11 +43,11 @@ def main():
     ap.add_argument("--top", type=int, default=40)
     args = ap.parse_args()
     dev = torch.device("cuda", 0)
-    cfg = so.vit_b16_config(use_mae=args.heads, use_kl=args.heads)
+    cfg = config.vit_b16(use_mae=args.heads, use_kl=args.heads)
     tc = argparse.Namespace(local_rank=0, rank=0, world_size=1, first_stage_layer=10, use_vision_mae_recon=args.heads,
                             use_seglabel=args.heads, precision="bf16")
     torch.manual_seed(0)
-    model = SegCLIP(fake_clip_state_dict(cfg), tc).to(dev).train()
+    model = SegCLIP(config.shape_state_dict(cfg), tc).to(dev).train()
     batch = {k: v.to(dev) for k, v in synthetic_batch(cfg, args.batch, 0, 0, args.heads).items()}
 
     def step():
