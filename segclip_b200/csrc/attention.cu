@@ -248,11 +248,17 @@ int sc_attention_fwd_mma(const sc_attn_desc* a, cudaStream_t st);
 int sc_attention_bwd_mma(const sc_attn_bwd_desc* g, float* delta, cudaStream_t st);
 bool sc_attn_tc_supported(const sc_attn_desc* a);
 int sc_attention_bwd_tc(const sc_attn_bwd_desc* g, float* delta, cudaStream_t st);
+int sc_attention_fwd_tc(const sc_attn_desc* a, cudaStream_t st);
 
 extern "C" int sc_attention_fwd(const sc_attn_desc* a, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
   int rc = check_desc(a, "sc_attention_fwd");
   if (rc) return rc;
+  {
+    static const int use_tc = [] { const char* e = getenv("SC_ATT_FWD_TC"); return e ? atoi(e) : 1; }();
+    if (use_tc && !a->force_generic && a->lse && sc_attn_tc_supported(a) && a->B <= 65535 && a->H <= 65535)
+      return sc_attention_fwd_tc(a, st);
+  }
   if (!a->force_generic && a->lse && sc_attn_mma_supported(a)) return sc_attention_fwd_mma(a, st);
   const size_t smem = sizeof(float) * ((size_t)2 * a->Lk * (a->hd + 1) + (size_t)ATT_WARPS * a->Lk + ATT_WARPS * 64);
   dim3 grid(a->H, a->B);

@@ -320,6 +320,234 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------------
+// tcgen05 / TMEM attention FORWARD (same scope: self-attention, head dim 64, L <= 256, optional causal mask): replaces
+// the bmm / softmax / bmm of nn.MultiheadAttention (modules/module_seg_vit.py:189, module_clip_ttransformer.py:46).
+//
+// Persistent CTAs, 2 per SM (80 KB smem, 256 TMEM columns each), looping over work items (query tile of 128, head,
+// sample): the next item's Q/K are TMA-loaded as soon as S has been computed and its V as soon as P V has retired, so
+// loads run under the softmax / epilogue of the current item, and the two co-resident CTAs fill each other's bubbles.
+// L <= 256 means a whole score row fits in TMEM: no online-softmax rescaling.
+//   S = Q_tile K^T           (A, B from smem, K-major; N = L rounded up to 16)          -> TMEM cols [0, N)
+//   softmax warps (thread = row): pass 1 row max, pass 2 p = exp2(s c - m c), row sum; P is written back as packed bf16
+//                            INTO TMEM over the consumed S columns [0, N/2)  (tcgen05.st)
+//   O = P V                  (A = P from TMEM, B = V from smem MN-major, N = 64)          -> TMEM cols [128, 192)
+//   epilogue: O / rowsum -> bf16 -> global; lse = m scale + ln(rowsum)
+// Warps 0-3: softmax + epilogue (TMEM lane quarter = warp); warp 4: TMA + MMA issue (one thread).
+constexpr int F_SM_Q = 0, F_SM_K = TILE * 128, F_SM_V = F_SM_K + OPER_BYTES;
+constexpr int F_SM_BAR = F_SM_V + OPER_BYTES;
+constexpr int F_SMEM_TOTAL = F_SM_BAR + 64;
+constexpr int F_THREADS = 5 * 32;
+constexpr uint32_t F_TM_O = 128, F_TM_COLS = 256;
+
+SC_DEVINL void tcgen05_mma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accum)
+      : "memory");
+}
+SC_DEVINL void tmem_st16(uint32_t taddr, const uint32_t* r) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+        "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+      : "memory");
+}
+
+template <bool CAUSAL>
+__global__ void __launch_bounds__(F_THREADS, 2)
+attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                   const __grid_constant__ CUtensorMap tmV, sc_attn_desc a) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  if ((smem_u32(smem) & 1023u) != 0u) __trap();
+  const uint32_t sbase = smem_u32(smem);
+  uint64_t* bars = (uint64_t*)(smem + F_SM_BAR);
+  uint64_t* bar_load = bars;       // TMA bytes landed
+  uint64_t* bar_s = bars + 1;      // S ready (commit)
+  uint64_t* bar_p = bars + 2;      // P written to TMEM (4 softmax warps)
+  uint64_t* bar_o = bars + 3;      // O ready (commit)
+  uint64_t* bar_v = bars + 4;      // V landed (needed only for P V: S and the softmax run under its flight)
+  uint32_t* tmem_slot = (uint32_t*)(bars + 6);
+
+  uint64_t* bar_free = bars + 5;   // O read out of TMEM by the 4 softmax warps: S / P / O columns reusable
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int L = a.Lq;
+  const int ntile = (L + TILE - 1) / TILE;
+  const int npad = (L + 15) & ~15;                 // MMA N of S, MMA K of P V
+  const int total = ntile * a.H * a.B;
+
+  auto issue_qk = [&](int w) {
+    const int qt = w % ntile, h = (w / ntile) % a.H, b = w / (ntile * a.H);
+    mbar_expect_tx(bar_load, TILE * 128 + ntile * TILE * 128);
+    tma_load_2d(&tmQ, bar_load, smem + F_SM_Q, h * HD, b * L + qt * TILE);
+    tma_load_2d(&tmK, bar_load, smem + F_SM_K, h * HD, b * L);
+  };
+  auto issue_v = [&](int w) {
+    const int h = (w / ntile) % a.H, b = w / (ntile * a.H);
+    mbar_expect_tx(bar_v, ntile * TILE * 128);
+    tma_load_2d(&tmV, bar_v, smem + F_SM_V, h * HD, b * L);
+  };
+
+  if (threadIdx.x == 4 * 32) {
+    mbar_init(bar_load, 1);
+    mbar_init(bar_s, 1);
+    mbar_init(bar_p, 4);
+    mbar_init(bar_o, 1);
+    mbar_init(bar_v, 1);
+    mbar_init(bar_free, 4);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    issue_qk(blockIdx.x);
+    issue_v(blockIdx.x);
+  }
+  if (warp == 4) {
+    __syncwarp();
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(F_TM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  if (warp == 4) {
+    if (lane == 0) {
+      const uint32_t id_s = make_idesc(npad, false, false);
+      constexpr uint32_t ID_PV = make_idesc(64, false, true);
+      uint32_t par = 0;
+      for (int w = blockIdx.x; w < total; w += gridDim.x, par ^= 1) {
+        const int qt = w % ntile;
+        const int wn = w + gridDim.x;
+        mbar_wait(bar_load, par);
+        tcgen05_fence_after();
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) {
+          const uint64_t dq_ = desc_sw128(sbase + F_SM_Q + kk * 32, 16, 1024);
+          const uint64_t dk_ = desc_sw128(sbase + F_SM_K + kk * 32, 16, 1024);
+          tcgen05_mma_f16(tmem, dq_, dk_, id_s, kk > 0);
+        }
+        tcgen05_commit(bar_s);
+        mbar_wait(bar_s, par);                       // Q / K consumed: the next item's may land
+        if (wn < total) issue_qk(wn);
+        mbar_wait(bar_v, par);
+        mbar_wait(bar_p, par);
+        tcgen05_fence_after();
+        const int nk = CAUSAL ? min(npad, ((qt * TILE + TILE + 15) & ~15)) >> 4 : npad >> 4;   // keys past the tile's last query: P = 0
+        for (int kk = 0; kk < nk; ++kk) {
+          const uint64_t dv_ = desc_sw128(sbase + F_SM_V + kk * 16 * 128, 8192, 1024);
+          tcgen05_mma_f16_ts(tmem + F_TM_O, tmem + kk * 8, dv_, ID_PV, kk > 0);
+        }
+        tcgen05_commit(bar_o);
+        mbar_wait(bar_o, par);                       // V consumed
+        if (wn < total) issue_v(wn);
+        mbar_wait(bar_free, par);                    // O read out: the accumulator columns may be overwritten
+        tcgen05_fence_after();
+      }
+    }
+  } else {
+    const uint32_t lane_off = (uint32_t)(warp * 32) << 16;
+    const int r = warp * 32 + lane;
+    const float c = a.scale * LOG2E_F;
+    uint32_t par = 0;
+    for (int w = blockIdx.x; w < total; w += gridDim.x, par ^= 1) {
+    const int qt = w % ntile, h = (w / ntile) % a.H, b = w / (ntile * a.H);
+    const int qi = qt * TILE + r;
+    const bool warp_live = qt * TILE + warp * 32 < L;
+    float m = -INFINITY, sum = 0.f;
+    mbar_wait(bar_s, par);
+    tcgen05_fence_after();
+    if (warp_live) {
+      const int kmax = CAUSAL ? min(L, qi + 1) : L;          // this row sees keys [0, kmax)
+      // Both passes keep the next 32-column TMEM load in flight while the current one is processed (two register
+      // buffers) and use 4 independent max / sum chains.
+      float bufa[32], bufb[32];                                // named buffers: static register indexing
+      // ---- pass 1: row max
+      float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+      auto max_chunk = [&](float (&s)[32], float (&nxt)[32], int c0) {
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        if (c0 + 32 < npad) tmem_ld32_nowait(tmem + lane_off + c0 + 32, nxt);
+        if (c0 + 32 <= kmax) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) m4[j & 3] = fmaxf(m4[j & 3], s[j]);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) m4[j & 3] = fmaxf(m4[j & 3], c0 + j < kmax ? s[j] : -INFINITY);
+        }
+      };
+      tmem_ld32_nowait(tmem + lane_off, bufa);
+      for (int c0 = 0; c0 < npad; c0 += 64) {
+        max_chunk(bufa, bufb, c0);
+        if (c0 + 32 < npad) max_chunk(bufb, bufa, c0 + 32);
+      }
+      m = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
+      const float mc = (m == -INFINITY) ? 0.f : m * c;        // dead rows (qi >= L) only
+      // ---- pass 2: p = exp2(s c - m c), row sum, packed bf16 P over the consumed S columns
+      float s4[4] = {0.f, 0.f, 0.f, 0.f};
+      auto exp_chunk = [&](float (&s)[32], float (&nxt)[32], int c0) {
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        // this chunk's P lands on columns [c0/2, c0/2+16), all below c0+32: it never touches S that is still unread
+        if (c0 + 32 < npad) tmem_ld32_nowait(tmem + lane_off + c0 + 32, nxt);
+        uint32_t pk[16];
+        if (c0 + 32 <= kmax) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 2) {
+            const float p0 = ex2f(fmaf(s[j], c, -mc)), p1 = ex2f(fmaf(s[j + 1], c, -mc));
+            s4[(j >> 1) & 3] += p0 + p1;
+            pk[j >> 1] = pack_bf16(p0, p1);
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; j += 2) {
+            const float p0 = c0 + j < kmax ? ex2f(fmaf(s[j], c, -mc)) : 0.f;
+            const float p1 = c0 + j + 1 < kmax ? ex2f(fmaf(s[j + 1], c, -mc)) : 0.f;
+            s4[(j >> 1) & 3] += p0 + p1;
+            pk[j >> 1] = pack_bf16(p0, p1);
+          }
+        }
+        tmem_st16(tmem + lane_off + (c0 >> 1), pk);
+      };
+      tmem_ld32_nowait(tmem + lane_off, bufa);
+      for (int c0 = 0; c0 < npad; c0 += 64) {
+        exp_chunk(bufa, bufb, c0);
+        if (c0 + 32 < npad) exp_chunk(bufb, bufa, c0 + 32);
+      }
+      sum = (s4[0] + s4[1]) + (s4[2] + s4[3]);
+      asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+    }
+    tcgen05_fence_before();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(bar_p);
+    mbar_wait(bar_o, par);
+    tcgen05_fence_after();
+    float o[64];
+    if (warp_live) {
+      tmem_ld32_nowait(tmem + lane_off + F_TM_O, o);
+      tmem_ld32_nowait(tmem + lane_off + F_TM_O + 32, o + 32);
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+    }
+    tcgen05_fence_before();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(bar_free);
+    if (warp_live && qi < L) {
+      const float inv = 1.0f / sum;
+      bf16* dst = (bf16*)a.o + (long)b * a.o_bs + (long)qi * a.o_rs + h * HD;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) store16_bf16(dst + 16 * j, o + 16 * j, inv);
+      a.lse[((long)b * a.H + h) * L + qi] = m * a.scale + logf(sum);
+    }
+    }   // item loop
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 4) {
+    tcgen05_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(F_TM_COLS) : "memory");
+  }
+}
+
 }  // namespace
 
 extern void sc_count_launch(int n);
@@ -357,6 +585,31 @@ int sc_attention_bwd_tc(const sc_attn_bwd_desc* g, float* delta, cudaStream_t st
     static bool cfg = false;
     if (!cfg) { SC_CUDA(cudaFuncSetAttribute(attn_bwd_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL)); cfg = true; }
     attn_bwd_tc_kernel<false><<<grid, TC_THREADS, SMEM_TOTAL, st>>>(tq, tk, tv, tdo, *g, delta);
+  }
+  SC_LAUNCH_CHECK();
+  return SC_OK;
+}
+
+int sc_attention_fwd_tc(const sc_attn_desc* a, cudaStream_t st) {
+  const int L = a->Lq, ntile = (L + TILE - 1) / TILE;
+  const long rows = (long)a->B * L;
+  CUtensorMap tq, tk, tv;
+  int rc;
+  if ((rc = sc_get_tensor_map(a->q, (uint64_t)a->H * HD, rows, a->q_rs, 64, TILE, &tq))) return rc;
+  if ((rc = sc_get_tensor_map(a->k, (uint64_t)a->H * HD, rows, a->k_rs, 64, ntile * TILE, &tk))) return rc;
+  if ((rc = sc_get_tensor_map(a->v, (uint64_t)a->H * HD, rows, a->v_rs, 64, ntile * TILE, &tv))) return rc;
+  sc_count_launch(1);
+  const long total = (long)ntile * a->H * a->B;
+  const long slots = 2L * sc_num_sms();
+  dim3 grid((unsigned)(total < slots ? total : slots));
+  if (a->causal) {
+    static bool cfg = false;
+    if (!cfg) { SC_CUDA(cudaFuncSetAttribute(attn_fwd_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, F_SMEM_TOTAL)); cfg = true; }
+    attn_fwd_tc_kernel<true><<<grid, F_THREADS, F_SMEM_TOTAL, st>>>(tq, tk, tv, *a);
+  } else {
+    static bool cfg = false;
+    if (!cfg) { SC_CUDA(cudaFuncSetAttribute(attn_fwd_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, F_SMEM_TOTAL)); cfg = true; }
+    attn_fwd_tc_kernel<false><<<grid, F_THREADS, F_SMEM_TOTAL, st>>>(tq, tk, tv, *a);
   }
   SC_LAUNCH_CHECK();
   return SC_OK;
