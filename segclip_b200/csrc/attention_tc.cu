@@ -117,6 +117,22 @@ SC_DEVINL void store16_bf16(bf16* dst, const float* v, float scale) {
   *(uint4*)(dst + 8) = w;
 }
 
+#ifdef SC_ATT_TRACE
+// debug build only: cycle-stamped events of CTA 0 (control warp + softmax warp 0), read back by sc_debug_attn_trace
+__device__ long long g_trace[2][512];
+__device__ int g_trace_n[2];
+#define TRACE(who, tag)                                                                     \
+  do {                                                                                      \
+    if (blockIdx.x == 0 && lane == 0 && g_trace_n[who] < 255) {                              \
+      const int i_ = g_trace_n[who]++;                                                      \
+      g_trace[who][2 * i_] = (tag);                                                         \
+      g_trace[who][2 * i_ + 1] = clock64();                                                 \
+    }                                                                                       \
+  } while (0)
+#else
+#define TRACE(who, tag) do { } while (0)
+#endif
+
 template <bool CAUSAL>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
@@ -127,47 +143,55 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   if ((smem_u32(smem) & 1023u) != 0u) __trap();
   const uint32_t sbase = smem_u32(smem);
   uint64_t* bars = (uint64_t*)(smem + SM_BAR);
-  uint64_t* bar_load = bars;          // TMA bytes landed
-  uint64_t* bar_s = bars + 1;         // S / dP ready (commit)
-  uint64_t* bar_p = bars + 2;         // P / dS tiles written, S / dP consumed (all softmax warps)
+  uint64_t* bar_load = bars;          // TMA bytes landed (one completion per item)
+  uint64_t* bar_s = bars + 1;         // S / dP ready (commit, one per pair)
+  uint64_t* bar_p = bars + 2;         // P / dS tiles written, S / dP consumed (all softmax warps, one per pair)
   uint64_t* bar_done = bars + 3;      // dV/dK/dQ MMAs of the pair retired (commit): tiles reusable
   uint64_t* bar_dkv = bars + 4;       // dV/dK of a key tile final (commit)
   uint64_t* bar_dkv_free = bars + 5;  // epilogue read dV/dK (all softmax warps)
+  uint64_t* bar_dq_free = bars + 6;   // epilogue read dQ (all softmax warps, one per item)
   uint32_t* tmem_slot = (uint32_t*)(bars + 8);
-  float* sLse = (float*)(smem + SM_LSE);
-  float* sDelta = sLse + ROWS;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int h = blockIdx.x, b = blockIdx.y;
   const int L = a.Lq;
   const int ntile = (L + TILE - 1) / TILE;
+  const int total = a.H * a.B;                       // work items: (sample, head), persistent CTAs stride over them
+  const int box_bytes = ntile * TILE * 128;
 
-  if (threadIdx.x == 0) {
+  // the four operands of an item -- rows b*L .. (+ntile*128), columns h*64 .. (+64)
+  // (called by the whole control warp: one elected lane issues)
+  auto issue_loads = [&](int w) {
+    const int h = w % a.H, b = w / a.H;
+    mbar_expect_tx_e(bar_load, 4 * box_bytes);
+    tma_load_2d_e(&tmQ, bar_load, smem + SM_Q, h * HD, b * L);
+    tma_load_2d_e(&tmK, bar_load, smem + SM_K, h * HD, b * L);
+    tma_load_2d_e(&tmV, bar_load, smem + SM_V, h * HD, b * L);
+    tma_load_2d_e(&tmdO, bar_load, smem + SM_DO, h * HD, b * L);
+  };
+  auto prefetch_l2 = [&](int w) {
+    const int h = w % a.H, b = w / a.H;
+    tma_prefetch_2d_e(&tmQ, h * HD, b * L);
+    tma_prefetch_2d_e(&tmK, h * HD, b * L);
+    tma_prefetch_2d_e(&tmV, h * HD, b * L);
+    tma_prefetch_2d_e(&tmdO, h * HD, b * L);
+  };
+
+  if (threadIdx.x == NSOFT * 32) {
     mbar_init(bar_load, 1);
     mbar_init(bar_s, 1);
     mbar_init(bar_p, NSOFT);
     mbar_init(bar_done, 1);
     mbar_init(bar_dkv, 1);
     mbar_init(bar_dkv_free, NSOFT);
+    mbar_init(bar_dq_free, NSOFT);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    // TMA right away: the four operands of this (sample, head) -- rows b*L .. (+ntile*128), columns h*64 .. (+64) --
-    // fly while TMEM is allocated and the lse / delta rows are staged
-    const int box_bytes = ntile * TILE * 128;
-    mbar_expect_tx(bar_load, 4 * box_bytes);
-    tma_load_2d(&tmQ, bar_load, smem + SM_Q, h * HD, b * L);
-    tma_load_2d(&tmK, bar_load, smem + SM_K, h * HD, b * L);
-    tma_load_2d(&tmV, bar_load, smem + SM_V, h * HD, b * L);
-    tma_load_2d(&tmdO, bar_load, smem + SM_DO, h * HD, b * L);
   }
   if (warp == NSOFT) {
+    __syncwarp();
+    issue_loads(blockIdx.x);          // flies while TMEM is allocated
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-  }
-  for (int i = threadIdx.x; i < ROWS; i += TC_THREADS) {
-    const long o = ((long)b * a.H + h) * L + i;
-    sLse[i] = i < L ? a.lse[o] * LOG2E_F : 0.f;
-    sDelta[i] = i < L ? delta[o] : 0.f;
   }
   tcgen05_fence_before();
   __syncthreads();
@@ -176,57 +200,85 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   const float c = a.scale * LOG2E_F;
 
   if (warp == NSOFT) {
-    if (lane == 0) {
-      mbar_wait(bar_load, 0);
-      tcgen05_fence_after();
+    {   // warp-uniform control flow; single-lane instructions are elected inside the *_e wrappers
       constexpr uint32_t ID_S = make_idesc(128, false, false);   // S, dP : A K-major, B K-major
       constexpr uint32_t ID_TT = make_idesc(64, true, true);     // dV, dK: A = tile read MN-major, B MN-major
       constexpr uint32_t ID_NT = make_idesc(64, false, true);    // dQ    : A = tile K-major,       B MN-major
-      uint32_t ph_p = 0, ph_free = 0;
-      for (int kt = 0; kt < ntile; ++kt) {
-        const int q_first = CAUSAL ? kt : 0;       // query tiles entirely before the key tile see nothing
-        for (int qt = q_first; qt < ntile; ++qt) {
-          // S = Q_qt K_kt^T and dP = dO_qt V_kt^T (their TMEM columns were released by bar_p of the previous pair)
+      auto issue_sdp = [&](int kt, int qt) {
+        // S^T = K_kt Q_qt^T and dP^T = V_kt dO_qt^T (their TMEM columns were released by bar_p of the previous pair)
 #pragma unroll
-          for (int kk = 0; kk < 4; ++kk) {
-            const uint64_t dq_ = desc_sw128(sbase + SM_Q + qt * 16384 + kk * 32, 16, 1024);
-            const uint64_t dk_ = desc_sw128(sbase + SM_K + kt * 16384 + kk * 32, 16, 1024);
-            tcgen05_mma_f16(tmem + TM_ST, dq_, dk_, ID_S, kk > 0);
-          }
-#pragma unroll
-          for (int kk = 0; kk < 4; ++kk) {
-            const uint64_t do_ = desc_sw128(sbase + SM_DO + qt * 16384 + kk * 32, 16, 1024);
-            const uint64_t dv_ = desc_sw128(sbase + SM_V + kt * 16384 + kk * 32, 16, 1024);
-            tcgen05_mma_f16(tmem + TM_DPT, do_, dv_, ID_S, kk > 0);
-          }
-          tcgen05_commit(bar_s);
-          mbar_wait(bar_p, ph_p);
-          ph_p ^= 1;
-          tcgen05_fence_after();
-          if (qt == q_first && kt > 0) {             // dV/dK accumulators of the previous key tile must have been read
-            mbar_wait(bar_dkv_free, ph_free);
-            ph_free ^= 1;
-            tcgen05_fence_after();
-          }
-#pragma unroll
-          for (int kq = 0; kq < 8; ++kq) {           // contraction over the 128 queries of this tile (tile rows)
-            // tile [query rows][key cols] read as MN-major A: 64-key chunks 16 KB apart (LBO), 8-query groups 1 KB (SBO)
-            const uint64_t dpa = desc_sw128(sbase + SM_PT + kq * 2048, 16384, 1024);
-            const uint64_t dsa = desc_sw128(sbase + SM_DST + kq * 2048, 16384, 1024);
-            const uint64_t dob = desc_sw128(sbase + SM_DO + (qt * TILE + kq * 16) * 128, 8192, 1024);
-            const uint64_t dqb = desc_sw128(sbase + SM_Q + (qt * TILE + kq * 16) * 128, 8192, 1024);
-            tcgen05_mma_f16(tmem + TM_DV, dpa, dob, ID_TT, (qt > q_first || kq > 0));
-            tcgen05_mma_f16(tmem + TM_DK, dsa, dqb, ID_TT, (qt > q_first || kq > 0));
-          }
-#pragma unroll
-          for (int kk = 0; kk < 8; ++kk) {           // contraction over the 128 keys of this tile (tile columns)
-            const uint64_t dsa = desc_sw128(sbase + SM_DST + (kk >> 2) * 16384 + (kk & 3) * 32, 16, 1024);
-            const uint64_t dkb = desc_sw128(sbase + SM_K + (kt * TILE + kk * 16) * 128, 8192, 1024);
-            tcgen05_mma_f16(tmem + TM_DQ + qt * 64, dsa, dkb, ID_NT, (kt > 0 || kk > 0));
-          }
-          tcgen05_commit(bar_done);
+        for (int kk = 0; kk < 4; ++kk) {
+          const uint64_t dq_ = desc_sw128(sbase + SM_Q + qt * 16384 + kk * 32, 16, 1024);
+          const uint64_t dk_ = desc_sw128(sbase + SM_K + kt * 16384 + kk * 32, 16, 1024);
+          tcgen05_mma_f16_e(tmem + TM_ST, dq_, dk_, ID_S, kk > 0);
         }
-        tcgen05_commit(bar_dkv);
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) {
+          const uint64_t do_ = desc_sw128(sbase + SM_DO + qt * 16384 + kk * 32, 16, 1024);
+          const uint64_t dv_ = desc_sw128(sbase + SM_V + kt * 16384 + kk * 32, 16, 1024);
+          tcgen05_mma_f16_e(tmem + TM_DPT, do_, dv_, ID_S, kk > 0);
+        }
+        tcgen05_commit_e(bar_s);
+      };
+      uint32_t ph_p = 0, ph_free = 0, ph_dq = 0, n_done = 0;
+      int it = 0;
+      for (int w = blockIdx.x; w < total; w += gridDim.x, ++it) {
+        const int wn = w + gridDim.x;
+        if (wn < total) prefetch_l2(wn);             // the next item's first touch goes to L2 while this one computes
+        TRACE(0, 1);
+        mbar_wait(bar_load, it & 1);
+        tcgen05_fence_after();
+        TRACE(0, 2);
+        issue_sdp(0, 0);
+        TRACE(0, 3);
+        for (int kt = 0; kt < ntile; ++kt) {
+          const int q_first = CAUSAL ? kt : 0;       // query tiles entirely before the key tile see nothing
+          for (int qt = q_first; qt < ntile; ++qt) {
+            mbar_wait(bar_p, ph_p);
+            ph_p ^= 1;
+            tcgen05_fence_after();
+            TRACE(0, 4);
+            // the next pair's S / dP go first: the softmax warps work on them while this pair's dV / dK / dQ run
+            if (qt + 1 < ntile) issue_sdp(kt, qt + 1);
+            else if (kt + 1 < ntile) issue_sdp(kt + 1, CAUSAL ? kt + 1 : 0);
+            if (qt == q_first && (kt > 0 || it > 0)) {   // dV/dK accumulators of the previous key tile must have been read
+              mbar_wait(bar_dkv_free, ph_free);
+              ph_free ^= 1;
+              tcgen05_fence_after();
+            }
+            if (kt == 0 && qt == q_first && it > 0) {    // ... and the previous item's dQ
+              mbar_wait(bar_dq_free, ph_dq);
+              ph_dq ^= 1;
+              tcgen05_fence_after();
+            }
+            TRACE(0, 5);
+#pragma unroll
+            for (int kq = 0; kq < 8; ++kq) {           // contraction over the 128 queries of this tile (tile rows)
+              // tile [query rows][key cols] read as MN-major A: 64-key chunks 16 KB apart (LBO), 8-query groups 1 KB (SBO)
+              const uint64_t dpa = desc_sw128(sbase + SM_PT + kq * 2048, 16384, 1024);
+              const uint64_t dsa = desc_sw128(sbase + SM_DST + kq * 2048, 16384, 1024);
+              const uint64_t dob = desc_sw128(sbase + SM_DO + (qt * TILE + kq * 16) * 128, 8192, 1024);
+              const uint64_t dqb = desc_sw128(sbase + SM_Q + (qt * TILE + kq * 16) * 128, 8192, 1024);
+              tcgen05_mma_f16_e(tmem + TM_DV, dpa, dob, ID_TT, (qt > q_first || kq > 0));
+              tcgen05_mma_f16_e(tmem + TM_DK, dsa, dqb, ID_TT, (qt > q_first || kq > 0));
+            }
+#pragma unroll
+            for (int kk = 0; kk < 8; ++kk) {           // contraction over the 128 keys of this tile (tile columns)
+              const uint64_t dsa = desc_sw128(sbase + SM_DST + (kk >> 2) * 16384 + (kk & 3) * 32, 16, 1024);
+              const uint64_t dkb = desc_sw128(sbase + SM_K + (kt * TILE + kk * 16) * 128, 8192, 1024);
+              tcgen05_mma_f16_e(tmem + TM_DQ + qt * 64, dsa, dkb, ID_NT, (kt > 0 || kk > 0));
+            }
+            tcgen05_commit_e(bar_done);
+            TRACE(0, 6);
+            ++n_done;
+          }
+          tcgen05_commit_e(bar_dkv);
+        }
+        if (wn < total) {
+          mbar_wait(bar_done, (n_done - 1) & 1);     // every MMA of this item has read its operands: reload them
+          TRACE(0, 7);
+          issue_loads(wn);
+        }
       }
     }
   } else {
@@ -235,81 +287,105 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     const uint32_t lane_off = (uint32_t)(quarter * 32) << 16;
     const int r = quarter * 32 + lane;                  // row inside the tile
     uint32_t ph_s = 0, ph_done = 0, ph_dkv = 0;
-    int pair = 0;
-    for (int kt = 0; kt < ntile; ++kt) {
-      const int q_first = CAUSAL ? kt : 0;
-      for (int qt = q_first; qt < ntile; ++qt, ++pair) {
-        const int qi = qt * TILE + r;                    // this thread's query
-        const int key0 = kt * TILE + cg * 32;            // first key of this warp's column group
-        const float lse2 = sLse[qi], dl = sDelta[qi];
-        mbar_wait(bar_s, ph_s);
-        ph_s ^= 1;
-        if (pair > 0) {                                  // the previous pair's MMAs must be done reading the tiles
-          mbar_wait(bar_done, ph_done);
-          ph_done ^= 1;
-        }
-        tcgen05_fence_after();
-        uint32_t pk[16], dk[16];                         // packed bf16 pairs of 32 columns
-        const bool warp_live = (qt * TILE + quarter * 32 < L) && key0 < L && (!CAUSAL || key0 <= qt * TILE + quarter * 32 + 31);
-        if (warp_live) {
-          float s[32], dp[32];
-          tmem_ld32_nowait(tmem + lane_off + TM_ST + cg * 32, s);
-          tmem_ld32_nowait(tmem + lane_off + TM_DPT + cg * 32, dp);
-          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+    bool first_pair = true;                             // very first pair of this CTA: no earlier MMAs read the tiles
+    for (int w = blockIdx.x; w < total; w += gridDim.x) {
+      const int h = w % a.H, b = w / a.H;
+      // this thread's two query rows (one per query tile): lse * log2e and delta straight from global (coalesced)
+      float lse2v[2], dlv[2];
 #pragma unroll
-          for (int j = 0; j < 32; j += 2) {
-            const int k0 = key0 + j;
-            const bool ok0 = qi < L && k0 < L && (!CAUSAL || k0 <= qi);
-            const bool ok1 = qi < L && k0 + 1 < L && (!CAUSAL || k0 + 1 <= qi);
-            const float p0 = ok0 ? ex2f(fmaf(s[j], c, -lse2)) : 0.f;
-            const float p1 = ok1 ? ex2f(fmaf(s[j + 1], c, -lse2)) : 0.f;
-            const float d0 = ok0 ? p0 * (dp[j] - dl) : 0.f, d1 = ok1 ? p1 * (dp[j + 1] - dl) : 0.f;
-            pk[j / 2] = pack_bf16(p0, p1);
-            dk[j / 2] = pack_bf16(d0, d1);
+      for (int t = 0; t < 2; ++t) {
+        const int qi = t * TILE + r;
+        const long o = ((long)b * a.H + h) * L + qi;
+        lse2v[t] = qi < L ? a.lse[o] * LOG2E_F : 0.f;
+        dlv[t] = qi < L ? delta[o] : 0.f;
+      }
+      for (int kt = 0; kt < ntile; ++kt) {
+        const int q_first = CAUSAL ? kt : 0;
+        for (int qt = q_first; qt < ntile; ++qt) {
+          const int qi = qt * TILE + r;                    // this thread's query
+          const int key0 = kt * TILE + cg * 32;            // first key of this warp's column group
+          const float lse2 = qt ? lse2v[1] : lse2v[0], dl = qt ? dlv[1] : dlv[0];
+          if (warp == 0) TRACE(1, 10);
+          mbar_wait(bar_s, ph_s);
+          ph_s ^= 1;
+          tcgen05_fence_after();
+          if (warp == 0) TRACE(1, 11);
+          uint32_t pk[16], dk[16];                         // packed bf16 pairs of 32 columns
+          const bool warp_live = (qt * TILE + quarter * 32 < L) && key0 < L && (!CAUSAL || key0 <= qt * TILE + quarter * 32 + 31);
+          if (warp_live) {
+            float s[32], dp[32];
+            tmem_ld32_nowait(tmem + lane_off + TM_ST + cg * 32, s);
+            tmem_ld32_nowait(tmem + lane_off + TM_DPT + cg * 32, dp);
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+            for (int j = 0; j < 32; j += 2) {
+              const int k0 = key0 + j;
+              const bool ok0 = qi < L && k0 < L && (!CAUSAL || k0 <= qi);
+              const bool ok1 = qi < L && k0 + 1 < L && (!CAUSAL || k0 + 1 <= qi);
+              const float p0 = ok0 ? ex2f(fmaf(s[j], c, -lse2)) : 0.f;
+              const float p1 = ok1 ? ex2f(fmaf(s[j + 1], c, -lse2)) : 0.f;
+              const float d0 = ok0 ? p0 * (dp[j] - dl) : 0.f, d1 = ok1 ? p1 * (dp[j + 1] - dl) : 0.f;
+              pk[j / 2] = pack_bf16(p0, p1);
+              dk[j / 2] = pack_bf16(d0, d1);
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) pk[j] = dk[j] = 0u;
           }
-        } else {
+          if (warp == 0) TRACE(1, 12);
+          if (!first_pair) {                               // the previous pair's MMAs must be done reading the tiles
+            mbar_wait(bar_done, ph_done);
+            ph_done ^= 1;
+          }
+          if (warp == 0) TRACE(1, 13);
+          first_pair = false;
+          // K-major 128B-swizzled tile [query rows][key cols]: k-block cg/2, 16-byte chunks (cg&1)*4 + j
+          const uint32_t rowp = sbase + SM_PT + (cg >> 1) * 16384 + r * 128, rowd = sbase + SM_DST + (cg >> 1) * 16384 + r * 128;
 #pragma unroll
-          for (int j = 0; j < 16; ++j) pk[j] = dk[j] = 0u;
+          for (int j = 0; j < 4; ++j) {
+            const uint32_t off = (uint32_t)((((cg & 1) * 4 + j) ^ (r & 7)) << 4);
+            sts128u(rowp + off, pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+            sts128u(rowd + off, dk[4 * j], dk[4 * j + 1], dk[4 * j + 2], dk[4 * j + 3]);
+          }
+          tcgen05_fence_before();
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the MMA (async proxy)
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bar_p);
+          if (warp == 0) TRACE(1, 14);
         }
-        // K-major 128B-swizzled tile [query rows][key cols]: k-block cg/2, 16-byte chunks (cg&1)*4 + j
-        const uint32_t rowp = sbase + SM_PT + (cg >> 1) * 16384 + r * 128, rowd = sbase + SM_DST + (cg >> 1) * 16384 + r * 128;
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const uint32_t off = (uint32_t)((((cg & 1) * 4 + j) ^ (r & 7)) << 4);
-          sts128u(rowp + off, pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
-          sts128u(rowd + off, dk[4 * j], dk[4 * j + 1], dk[4 * j + 2], dk[4 * j + 3]);
+        // ---- dV / dK of this key tile (TMEM lanes = keys); this warp handles 16 of the 64 head-dim columns
+        mbar_wait(bar_dkv, ph_dkv);
+        ph_dkv ^= 1;
+        tcgen05_fence_after();
+        if (warp == 0) TRACE(1, 15);
+        {
+          float v[16], k[16];
+          tmem_ld16(tmem + lane_off + TM_DV + cg * 16, v);
+          tmem_ld16(tmem + lane_off + TM_DK + cg * 16, k);
+          tcgen05_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bar_dkv_free);
+          const int key = kt * TILE + r;
+          if (key < L) {
+            store16_bf16((bf16*)gd.d_v + (long)b * a.v_bs + (long)key * a.v_rs + h * HD + cg * 16, v, 1.0f);
+            store16_bf16((bf16*)gd.d_k + (long)b * a.k_bs + (long)key * a.k_rs + h * HD + cg * 16, k, a.scale);
+          }
         }
-        tcgen05_fence_before();
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the MMA (async proxy)
-        __syncwarp();
-        if (lane == 0) mbar_arrive(bar_p);
+        if (warp == 0) TRACE(1, 16);
       }
-      // ---- dV / dK of this key tile (TMEM lanes = keys); this warp handles 16 of the 64 head-dim columns
-      mbar_wait(bar_dkv, ph_dkv);
-      ph_dkv ^= 1;
-      tcgen05_fence_after();
+      // ---- dQ (TMEM lanes = queries): bar_dkv of the last key tile was committed after every MMA of the item
       {
-        float v[16], k[16];
-        tmem_ld16(tmem + lane_off + TM_DV + cg * 16, v);
-        tmem_ld16(tmem + lane_off + TM_DK + cg * 16, k);
+        float v0[16], v1[16];
+        tmem_ld16(tmem + lane_off + TM_DQ + cg * 16, v0);
+        if (ntile > 1) tmem_ld16(tmem + lane_off + TM_DQ + 64 + cg * 16, v1);
         tcgen05_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(bar_dkv_free);
-        const int key = kt * TILE + r;
-        if (key < L) {
-          store16_bf16((bf16*)gd.d_v + (long)b * a.v_bs + (long)key * a.v_rs + h * HD + cg * 16, v, 1.0f);
-          store16_bf16((bf16*)gd.d_k + (long)b * a.k_bs + (long)key * a.k_rs + h * HD + cg * 16, k, a.scale);
-        }
+        if (lane == 0) mbar_arrive(bar_dq_free);
+        if (r < L) store16_bf16((bf16*)gd.d_q + (long)b * a.q_bs + (long)r * a.q_rs + h * HD + cg * 16, v0, a.scale);
+        if (ntile > 1 && TILE + r < L)
+          store16_bf16((bf16*)gd.d_q + (long)b * a.q_bs + (long)(TILE + r) * a.q_rs + h * HD + cg * 16, v1, a.scale);
+        if (warp == 0) TRACE(1, 17);
       }
-    }
-    // ---- dQ (TMEM lanes = queries); the last bar_done covers every MMA
-    mbar_wait(bar_done, ph_done);
-    tcgen05_fence_after();
-    for (int qt = 0; qt < ntile; ++qt) {
-      float v[16];
-      tmem_ld16(tmem + lane_off + TM_DQ + qt * 64 + cg * 16, v);
-      const int qi = qt * TILE + r;
-      if (qi < L) store16_bf16((bf16*)gd.d_q + (long)b * a.q_bs + (long)qi * a.q_rs + h * HD + cg * 16, v, a.scale);
     }
   }
   tcgen05_fence_before();
@@ -319,7 +395,6 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
   }
 }
-
 
 // ---------------------------------------------------------------------------------------------------------------------
 // tcgen05 / TMEM attention FORWARD (same scope: self-attention, head dim 64, L <= 256, optional causal mask): replaces
@@ -576,7 +651,8 @@ int sc_attention_bwd_tc(const sc_attn_bwd_desc* g, float* delta, cudaStream_t st
   const long n = rows * a->H;
   attn_delta_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>((const bf16*)a->o, (const bf16*)g->d_o, a->o_bs, a->o_rs, a->B,
                                                                  a->H, L, delta);
-  dim3 grid(a->H, a->B);
+  const long items = (long)a->H * a->B;
+  dim3 grid((unsigned)(items < sc_num_sms() ? items : sc_num_sms()));       // persistent: one CTA per SM
   if (a->causal) {
     static bool cfg = false;
     if (!cfg) { SC_CUDA(cudaFuncSetAttribute(attn_bwd_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL)); cfg = true; }
@@ -614,3 +690,14 @@ int sc_attention_fwd_tc(const sc_attn_desc* a, cudaStream_t st) {
   SC_LAUNCH_CHECK();
   return SC_OK;
 }
+
+#ifdef SC_ATT_TRACE
+extern "C" int sc_debug_attn_trace(long long* out, int* n) {
+  cudaDeviceSynchronize();
+  cudaMemcpyFromSymbol(out, g_trace, sizeof(long long) * 2 * 512);
+  cudaMemcpyFromSymbol(n, g_trace_n, sizeof(int) * 2);
+  int z[2] = {0, 0};
+  cudaMemcpyToSymbol(g_trace_n, z, sizeof(z));
+  return 0;
+}
+#endif

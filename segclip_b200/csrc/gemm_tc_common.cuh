@@ -68,6 +68,58 @@ SC_DEVINL void tcgen05_mma_f16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b
       ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accum)
       : "memory");
 }
+// ---- warp-uniform issue: the whole warp runs the producer / MMA loop (addresses and descriptors stay in uniform
+// registers) and one elected lane executes the instruction.  With `if (lane == 0) { loop }` ptxas cannot prove
+// uniformity and wraps every UTCHMMA in ~20 instructions of R2UR.BROADCAST / ELECT / BRA.U.ANY, which is slower than
+// the N = 64 MMAs themselves.  elect.sync with a full mask always names the same lane, so tcgen05.commit still tracks
+// the MMAs issued before it.
+SC_DEVINL void tcgen05_mma_f16_e(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n\t.reg .pred p, e;\n\t"
+      "elect.sync _|e, 0xffffffff;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "@e tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accum)
+      : "memory");
+}
+SC_DEVINL void tcgen05_mma_f16_ts_e(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n\t.reg .pred p, e;\n\t"
+      "elect.sync _|e, 0xffffffff;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "@e tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accum)
+      : "memory");
+}
+SC_DEVINL void tcgen05_commit_e(uint64_t* bar) {
+  asm volatile(
+      "{\n\t.reg .pred e;\n\t"
+      "elect.sync _|e, 0xffffffff;\n\t"
+      "@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}" ::"r"(smem_u32(bar))
+      : "memory");
+}
+SC_DEVINL void mbar_expect_tx_e(uint64_t* bar, uint32_t bytes) {
+  asm volatile(
+      "{\n\t.reg .pred e;\n\t"
+      "elect.sync _|e, 0xffffffff;\n\t"
+      "@e mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n\t}" ::"r"(smem_u32(bar)), "r"(bytes)
+      : "memory");
+}
+SC_DEVINL void tma_load_2d_e(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1) {
+  asm volatile(
+      "{\n\t.reg .pred e;\n\t"
+      "elect.sync _|e, 0xffffffff;\n\t"
+      "@e cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];\n\t}"
+      ::"r"(smem_u32(dst)), "l"((uint64_t)map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+SC_DEVINL void tma_prefetch_2d_e(const CUtensorMap* map, int c0, int c1) {
+  asm volatile(
+      "{\n\t.reg .pred e;\n\t"
+      "elect.sync _|e, 0xffffffff;\n\t"
+      "@e cp.async.bulk.prefetch.tensor.2d.L2.global [%0, {%1, %2}];\n\t}" ::"l"((uint64_t)map), "r"(c0), "r"(c1)
+      : "memory");
+}
 SC_DEVINL void tmem_ld32(uint32_t taddr, float* v) {
   uint32_t* r = (uint32_t*)v;
   asm volatile(
