@@ -46,6 +46,7 @@ class ClockSampler:
 
     def __init__(self, index):
         self.rows, self.proc, self.index = [], None, index
+        self.t0 = self.t1 = None
 
     def start(self):
         try:
@@ -57,18 +58,32 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([x.strip() for x in line.split(",")])
+            self.rows.append([time.time()] + [x.strip() for x in line.split(",")])
+
+    def wait_ready(self, timeout=10.0):
+        """nvidia-smi takes a moment to deliver its first sample: do not start the timed region before it."""
+        t = time.time()
+        while self.proc is not None and not self.rows and time.time() - t < timeout:
+            time.sleep(0.05)
+
+    def mark(self, begin):
+        if begin:
+            self.t0 = time.time()
+        else:
+            self.t1 = time.time()
 
     def stop(self):
         if self.proc is None:
             return None
         self.proc.terminate()
-        sm = sorted(int(float(r[1])) for r in self.rows if len(r) >= 8)
+        rows = [r[1:] for r in self.rows if len(r) >= 9 and (self.t0 is None or r[0] >= self.t0) and
+                (self.t1 is None or r[0] <= self.t1 + 0.15)]
+        sm = sorted(int(float(r[1])) for r in rows)
         if not sm:
             return None
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({n for r in self.rows if len(r) >= 8 for n, v in zip(names, r[4:8]) if v.lower().startswith("active")})
-        return dict(sm_mhz=sm[len(sm) // 2], sm_max_mhz=int(float(self.rows[0][2])), reasons=reasons, samples=len(sm))
+        reasons = sorted({n for r in rows for n, v in zip(names, r[4:8]) if v.lower().startswith("active")})
+        return dict(sm_mhz=sm[len(sm) // 2], sm_max_mhz=int(float(rows[0][2])), reasons=reasons, samples=len(sm))
 
 
 def synthetic_batch(cfg, B, seed, rank, heads):
@@ -209,17 +224,22 @@ def main():
             ms = float(t)
         return ms
 
-    for _ in range(args.warmup):
-        step(resident, False)
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
+    for _ in range(args.warmup):
+        step(resident, False)
+    if rank == 0:
+        sampler.wait_ready()
+        sampler.mark(True)
     l0 = _lib.launch_count()
     ms = timed(resident, False, args.steps)
     launches = (_lib.launch_count() - l0) // args.steps
-    clocks = sampler.stop() if rank == 0 else None
     step(pinned, True)
-    ms_e2e = timed(pinned, True, args.steps)
+    ms_e2e = timed(pinned, True, args.steps)          # clocks are sampled over both timed regions
+    if rank == 0:
+        sampler.mark(False)
+    clocks = sampler.stop() if rank == 0 else None
 
     # dominant kernel (tcgen05 GEMM): achieved TFLOP/s over all its launches of one step, CUDA events
     gemm = model._engine.profile_gemm(B) if rank == 0 else None
@@ -246,7 +266,8 @@ def main():
         "step_tensor_frac": {"achieved_tflops_per_gpu": value / world * gf / 1e3, "peak": pk["tflops"],
                              "frac": value / world * gf / 1e3 / pk["tflops"], "flops_per_pair_gf": gf},
         "roofline": {"bound": "tensor", "achieved": gemm["tflops"], "peak": pk["tflops"], "unit": "TFLOP/s",
-                     "frac": gemm["tflops"] / pk["tflops"], "traffic": None, "kernel": "gemm_tc_kernel (tcgen05)",
+                     "frac": gemm["tflops"] / pk["tflops"], "traffic": gemm_traffic(args),
+                     "kernel": "gemm_tc2_kernel (tcgen05 cta_group::2, all launches of one step)",
                      "launches_per_step": gemm["launches"], "share_of_step": gemm["ms"] / ms, "peak_source": pk["src"]},
     }
     if world == 1 and not args.no_cpu_baseline:
@@ -254,6 +275,15 @@ def main():
     print(json.dumps(out))
     if world > 1:
         dist.barrier()
+
+
+def gemm_traffic(args):
+    """Average DRAM bytes (read + write) per gemm_tc2_kernel launch of this workload, from the committed ncu pass
+    (profiles/r1_gemm_traffic.json, written by tools/summarize_launches.py --traffic); None for other workloads."""
+    path = os.path.join(ROOT, "profiles", "r1_gemm_traffic.json")
+    if args.model != "vitb16" or args.heads or args.batch != 256 or not os.path.exists(path):
+        return None
+    return json.load(open(path)).get("dram_bytes_per_launch")
 
 
 def cpu_baseline(args):
