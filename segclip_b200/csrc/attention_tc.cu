@@ -288,17 +288,41 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     const int r = quarter * 32 + lane;                  // row inside the tile
     uint32_t ph_s = 0, ph_done = 0, ph_dkv = 0;
     bool first_pair = true;                             // very first pair of this CTA: no earlier MMAs read the tiles
-    for (int w = blockIdx.x; w < total; w += gridDim.x) {
+    // this thread's two query rows (one per query tile): lse and delta straight from global (coalesced); the next
+    // item's values are requested before the epilogues of the current one, so their latency is never exposed
+    float lse_c[2], dl_c[2], lse_n[2] = {0.f, 0.f}, dl_n[2] = {0.f, 0.f};
+    auto load_rows = [&](int w, float (&ls)[2], float (&dl)[2]) {
       const int h = w % a.H, b = w / a.H;
-      // this thread's two query rows (one per query tile): lse * log2e and delta straight from global (coalesced)
-      float lse2v[2], dlv[2];
 #pragma unroll
       for (int t = 0; t < 2; ++t) {
         const int qi = t * TILE + r;
         const long o = ((long)b * a.H + h) * L + qi;
-        lse2v[t] = qi < L ? a.lse[o] * LOG2E_F : 0.f;
-        dlv[t] = qi < L ? delta[o] : 0.f;
+        ls[t] = qi < L ? a.lse[o] : 0.f;
+        dl[t] = qi < L ? delta[o] : 0.f;
       }
+    };
+    auto dkv_epilogue = [&](int kt, int h, int b) {
+      // dV / dK of a key tile (TMEM lanes = keys); this warp handles 16 of the 64 head-dim columns
+      mbar_wait(bar_dkv, ph_dkv);
+      ph_dkv ^= 1;
+      tcgen05_fence_after();
+      float v[16], kk[16];
+      tmem_ld16(tmem + lane_off + TM_DV + cg * 16, v);
+      tmem_ld16(tmem + lane_off + TM_DK + cg * 16, kk);
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_dkv_free);
+      const int key = kt * TILE + r;
+      if (key < L) {
+        store16_bf16((bf16*)gd.d_v + (long)b * a.v_bs + (long)key * a.v_rs + h * HD + cg * 16, v, 1.0f);
+        store16_bf16((bf16*)gd.d_k + (long)b * a.k_bs + (long)key * a.k_rs + h * HD + cg * 16, kk, a.scale);
+      }
+    };
+    if ((int)blockIdx.x < total) load_rows(blockIdx.x, lse_c, dl_c);
+    for (int w = blockIdx.x; w < total; w += gridDim.x) {
+      const int h = w % a.H, b = w / a.H;
+      const float lse2v[2] = {lse_c[0] * LOG2E_F, lse_c[1] * LOG2E_F};
+      const float dlv[2] = {dl_c[0], dl_c[1]};
       for (int kt = 0; kt < ntile; ++kt) {
         const int q_first = CAUSAL ? kt : 0;
         for (int qt = q_first; qt < ntile; ++qt) {
@@ -352,27 +376,17 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
           __syncwarp();
           if (lane == 0) mbar_arrive(bar_p);
           if (warp == 0) TRACE(1, 14);
-        }
-        // ---- dV / dK of this key tile (TMEM lanes = keys); this warp handles 16 of the 64 head-dim columns
-        mbar_wait(bar_dkv, ph_dkv);
-        ph_dkv ^= 1;
-        tcgen05_fence_after();
-        if (warp == 0) TRACE(1, 15);
-        {
-          float v[16], k[16];
-          tmem_ld16(tmem + lane_off + TM_DV + cg * 16, v);
-          tmem_ld16(tmem + lane_off + TM_DK + cg * 16, k);
-          tcgen05_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(bar_dkv_free);
-          const int key = kt * TILE + r;
-          if (key < L) {
-            store16_bf16((bf16*)gd.d_v + (long)b * a.v_bs + (long)key * a.v_rs + h * HD + cg * 16, v, 1.0f);
-            store16_bf16((bf16*)gd.d_k + (long)b * a.k_bs + (long)key * a.k_rs + h * HD + cg * 16, k, a.scale);
+          // the previous key tile's dV / dK are read out only now: this pair's softmax went first, so the MMA pipe has
+          // its next tiles while the accumulators are drained and stored
+          if (qt == q_first && kt > 0) {
+            dkv_epilogue(kt - 1, h, b);
+            if (warp == 0) TRACE(1, 16);
           }
         }
-        if (warp == 0) TRACE(1, 16);
       }
+      if (w + (int)gridDim.x < total) load_rows(w + gridDim.x, lse_n, dl_n);
+      dkv_epilogue(ntile - 1, h, b);
+      if (warp == 0) TRACE(1, 16);
       // ---- dQ (TMEM lanes = queries): bar_dkv of the last key tile was committed after every MMA of the item
       {
         float v0[16], v1[16];
@@ -386,6 +400,8 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
           store16_bf16((bf16*)gd.d_q + (long)b * a.q_bs + (long)(TILE + r) * a.q_rs + h * HD + cg * 16, v1, a.scale);
         if (warp == 0) TRACE(1, 17);
       }
+      lse_c[0] = lse_n[0]; lse_c[1] = lse_n[1];
+      dl_c[0] = dl_n[0]; dl_c[1] = dl_n[1];
     }
   }
   tcgen05_fence_before();
