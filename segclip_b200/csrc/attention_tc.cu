@@ -12,7 +12,7 @@
 //   dK_kt += dS^T Q_qt          (A K-major tile,  B = Q  MN-major, N = 64) -> TMEM cols [320,384)
 //   dQ_qt += dS   K_kt          (A = dS^T tile read MN-major, B = K MN-major, N = 64) -> TMEM cols [384,448) / [448,512)
 // TMEM is used completely (512 columns).  Warps 0-7: softmax + epilogues (lane quarter = warp % 4, column half = warp / 4);
-// warp 8: TMA + MMA issue (one thread).
+// warp 16: MMA issue, warp 17: TMA producer (one elected lane each).
 #include "gemm_tc_common.cuh"
 
 namespace {
@@ -29,7 +29,7 @@ constexpr int SM_LSE = SM_DST + PT_BYTES;      // float[256] lse*log2e, float[25
 constexpr int SM_BAR = SM_LSE + 2 * ROWS * 4;
 constexpr int SMEM_TOTAL = SM_BAR + 128;
 constexpr int NSOFT = 16;                      // softmax / epilogue warps: 4 per TMEM lane quarter x 32 columns
-constexpr int TC_THREADS = (NSOFT + 1) * 32;
+constexpr int TC_THREADS = (NSOFT + 2) * 32;   // + MMA-issue warp + TMA producer warp
 constexpr float LOG2E_F = 1.4426950408889634f;
 
 constexpr uint32_t TM_ST = 0, TM_DPT = 128, TM_DV = 256, TM_DK = 320, TM_DQ = 384;
@@ -143,41 +143,41 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   if ((smem_u32(smem) & 1023u) != 0u) __trap();
   const uint32_t sbase = smem_u32(smem);
   uint64_t* bars = (uint64_t*)(smem + SM_BAR);
-  uint64_t* bar_load = bars;          // TMA bytes landed (one completion per item)
+  uint64_t* bar_load = bars;          // TMA bytes of the first 128 rows of Q, K, V, dO landed (one completion per item)
+  uint64_t* bar_load1 = bars + 7;     // ... of rows 128..255 (items with two tiles)
+  uint64_t* bar_free0 = bars + 8;     // commit: MMAs that read the first row group have retired (one per item with >1 pair)
+  uint64_t* bar_free1 = bars + 9;     // commit: every MMA of the item has retired (one per item)
   uint64_t* bar_s = bars + 1;         // S / dP ready (commit, one per pair)
   uint64_t* bar_p = bars + 2;         // P / dS tiles written, S / dP consumed (all softmax warps, one per pair)
   uint64_t* bar_done = bars + 3;      // dV/dK/dQ MMAs of the pair retired (commit): tiles reusable
   uint64_t* bar_dkv = bars + 4;       // dV/dK of a key tile final (commit)
   uint64_t* bar_dkv_free = bars + 5;  // epilogue read dV/dK (all softmax warps)
   uint64_t* bar_dq_free = bars + 6;   // epilogue read dQ (all softmax warps, one per item)
-  uint32_t* tmem_slot = (uint32_t*)(bars + 8);
+  uint32_t* tmem_slot = (uint32_t*)(bars + 10);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int L = a.Lq;
   const int ntile = (L + TILE - 1) / TILE;
   const int total = a.H * a.B;                       // work items: (sample, head), persistent CTAs stride over them
-  const int box_bytes = ntile * TILE * 128;
 
-  // the four operands of an item -- rows b*L .. (+ntile*128), columns h*64 .. (+64)
+  // The operands of an item -- rows b*L .. (+ntile*128), columns h*64 .. (+64) -- arrive as two groups of 128-row
+  // boxes: the first rows of Q/K/V/dO are last read by the second-to-last pair, so the next item's first group is
+  // loaded under the last pair and only the second group waits for the item's final MMAs.
   // (called by the whole control warp: one elected lane issues)
-  auto issue_loads = [&](int w) {
+  auto issue_group = [&](int w, int g) {
     const int h = w % a.H, b = w / a.H;
-    mbar_expect_tx_e(bar_load, 4 * box_bytes);
-    tma_load_2d_e(&tmQ, bar_load, smem + SM_Q, h * HD, b * L);
-    tma_load_2d_e(&tmK, bar_load, smem + SM_K, h * HD, b * L);
-    tma_load_2d_e(&tmV, bar_load, smem + SM_V, h * HD, b * L);
-    tma_load_2d_e(&tmdO, bar_load, smem + SM_DO, h * HD, b * L);
+    uint64_t* bar = g ? bar_load1 : bar_load;
+    mbar_expect_tx_e(bar, 4 * TILE * 128);
+    tma_load_2d_e(&tmQ, bar, smem + SM_Q + g * 16384, h * HD, b * L + g * TILE);
+    tma_load_2d_e(&tmK, bar, smem + SM_K + g * 16384, h * HD, b * L + g * TILE);
+    tma_load_2d_e(&tmV, bar, smem + SM_V + g * 16384, h * HD, b * L + g * TILE);
+    tma_load_2d_e(&tmdO, bar, smem + SM_DO + g * 16384, h * HD, b * L + g * TILE);
   };
-  auto prefetch_l2 = [&](int w) {
-    const int h = w % a.H, b = w / a.H;
-    tma_prefetch_2d_e(&tmQ, h * HD, b * L);
-    tma_prefetch_2d_e(&tmK, h * HD, b * L);
-    tma_prefetch_2d_e(&tmV, h * HD, b * L);
-    tma_prefetch_2d_e(&tmdO, h * HD, b * L);
-  };
-
   if (threadIdx.x == NSOFT * 32) {
     mbar_init(bar_load, 1);
+    mbar_init(bar_load1, 1);
+    mbar_init(bar_free0, 1);
+    mbar_init(bar_free1, 1);
     mbar_init(bar_s, 1);
     mbar_init(bar_p, NSOFT);
     mbar_init(bar_done, 1);
@@ -189,7 +189,8 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   }
   if (warp == NSOFT) {
     __syncwarp();
-    issue_loads(blockIdx.x);          // flies while TMEM is allocated
+    issue_group(blockIdx.x, 0);       // flies while TMEM is allocated
+    if (ntile > 1) issue_group(blockIdx.x, 1);
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
@@ -220,11 +221,13 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         }
         tcgen05_commit_e(bar_s);
       };
-      uint32_t ph_p = 0, ph_free = 0, ph_dq = 0, n_done = 0;
+      uint32_t ph_p = 0, ph_free = 0, ph_dq = 0;
       int it = 0;
       for (int w = blockIdx.x; w < total; w += gridDim.x, ++it) {
         const int wn = w + gridDim.x;
-        if (wn < total) prefetch_l2(wn);             // the next item's first touch goes to L2 while this one computes
+        const int np = CAUSAL ? ntile * (ntile + 1) / 2 : ntile * ntile;   // pairs of this item
+        int pi = 0;
+        bool have1 = ntile == 1;                     // second operand group waited for
         TRACE(0, 1);
         mbar_wait(bar_load, it & 1);
         tcgen05_fence_after();
@@ -239,6 +242,11 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
             tcgen05_fence_after();
             TRACE(0, 4);
             // the next pair's S / dP go first: the softmax warps work on them while this pair's dV / dK / dQ run
+            if (!have1 && pi + 1 < np) {               // every pair after the first touches rows 128..255
+              mbar_wait(bar_load1, it & 1);
+              tcgen05_fence_after();
+              have1 = true;
+            }
             if (qt + 1 < ntile) issue_sdp(kt, qt + 1);
             else if (kt + 1 < ntile) issue_sdp(kt + 1, CAUSAL ? kt + 1 : 0);
             if (qt == q_first && (kt > 0 || it > 0)) {   // dV/dK accumulators of the previous key tile must have been read
@@ -270,15 +278,32 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
             }
             tcgen05_commit_e(bar_done);
             TRACE(0, 6);
-            ++n_done;
+            ++pi;
+            // the last pair reads only rows 128..255: once everything up to the second-to-last pair has retired the
+            // producer warp may overwrite rows 0..127 with the next item
+            if (pi == np - 1) tcgen05_commit_e(bar_free0);
           }
           tcgen05_commit_e(bar_dkv);
         }
-        if (wn < total) {
-          mbar_wait(bar_done, (n_done - 1) & 1);     // every MMA of this item has read its operands: reload them
-          TRACE(0, 7);
-          issue_loads(wn);
-        }
+        tcgen05_commit_e(bar_free1);
+        TRACE(0, 7);
+      }
+    }
+  } else if (warp == NSOFT + 1) {
+    // ---------------- TMA producer: a UTMALDG blocks its warp for ~800 cycles per 16 KB box while the TMA unit drains its
+    // queue (measured with SC_ATT_TRACE), so the loads have their own warp and never delay MMA issue
+    const int np = CAUSAL ? ntile * (ntile + 1) / 2 : ntile * ntile;
+    int it = 0;
+    for (int w = blockIdx.x; w + (int)gridDim.x < total; w += gridDim.x, ++it) {
+      const int wn = w + gridDim.x;
+      if (np > 1) {
+        mbar_wait(bar_free0, it & 1);
+        issue_group(wn, 0);
+        mbar_wait(bar_free1, it & 1);
+        issue_group(wn, 1);
+      } else {
+        mbar_wait(bar_free1, it & 1);
+        issue_group(wn, 0);
       }
     }
   } else {
@@ -341,16 +366,27 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
             tmem_ld32_nowait(tmem + lane_off + TM_ST + cg * 32, s);
             tmem_ld32_nowait(tmem + lane_off + TM_DPT + cg * 32, dp);
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            const int row_lo = qt * TILE + quarter * 32;       // the warp's first query
+            const bool full = row_lo + 31 < L && key0 + 31 < L && (!CAUSAL || key0 + 31 <= row_lo);   // warp-uniform
+            if (full) {                                        // interior block: no masks
 #pragma unroll
-            for (int j = 0; j < 32; j += 2) {
-              const int k0 = key0 + j;
-              const bool ok0 = qi < L && k0 < L && (!CAUSAL || k0 <= qi);
-              const bool ok1 = qi < L && k0 + 1 < L && (!CAUSAL || k0 + 1 <= qi);
-              const float p0 = ok0 ? ex2f(fmaf(s[j], c, -lse2)) : 0.f;
-              const float p1 = ok1 ? ex2f(fmaf(s[j + 1], c, -lse2)) : 0.f;
-              const float d0 = ok0 ? p0 * (dp[j] - dl) : 0.f, d1 = ok1 ? p1 * (dp[j + 1] - dl) : 0.f;
-              pk[j / 2] = pack_bf16(p0, p1);
-              dk[j / 2] = pack_bf16(d0, d1);
+              for (int j = 0; j < 32; j += 2) {
+                const float p0 = ex2f(fmaf(s[j], c, -lse2)), p1 = ex2f(fmaf(s[j + 1], c, -lse2));
+                pk[j / 2] = pack_bf16(p0, p1);
+                dk[j / 2] = pack_bf16(p0 * (dp[j] - dl), p1 * (dp[j + 1] - dl));
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; j += 2) {
+                const int k0 = key0 + j;
+                const bool ok0 = qi < L && k0 < L && (!CAUSAL || k0 <= qi);
+                const bool ok1 = qi < L && k0 + 1 < L && (!CAUSAL || k0 + 1 <= qi);
+                const float p0 = ok0 ? ex2f(fmaf(s[j], c, -lse2)) : 0.f;
+                const float p1 = ok1 ? ex2f(fmaf(s[j + 1], c, -lse2)) : 0.f;
+                const float d0 = ok0 ? p0 * (dp[j] - dl) : 0.f, d1 = ok1 ? p1 * (dp[j + 1] - dl) : 0.f;
+                pk[j / 2] = pack_bf16(p0, p1);
+                dk[j / 2] = pack_bf16(d0, d1);
+              }
             }
           } else {
 #pragma unroll
@@ -658,11 +694,11 @@ int sc_attention_bwd_tc(const sc_attn_bwd_desc* g, float* delta, cudaStream_t st
   const long rows = (long)a->B * L;
   CUtensorMap tq, tk, tv, tdo;
   int rc;
-  // 2-D maps over the [B*L, H*64] column slices; box = 64 columns x ntile*128 rows, zero fill past the last row
-  if ((rc = sc_get_tensor_map(a->q, (uint64_t)a->H * HD, rows, a->q_rs, 64, ntile * TILE, &tq))) return rc;
-  if ((rc = sc_get_tensor_map(a->k, (uint64_t)a->H * HD, rows, a->k_rs, 64, ntile * TILE, &tk))) return rc;
-  if ((rc = sc_get_tensor_map(a->v, (uint64_t)a->H * HD, rows, a->v_rs, 64, ntile * TILE, &tv))) return rc;
-  if ((rc = sc_get_tensor_map(g->d_o, (uint64_t)a->H * HD, rows, a->o_rs, 64, ntile * TILE, &tdo))) return rc;
+  // 2-D maps over the [B*L, H*64] column slices; box = 64 columns x 128 rows, zero fill past the last row
+  if ((rc = sc_get_tensor_map(a->q, (uint64_t)a->H * HD, rows, a->q_rs, 64, TILE, &tq))) return rc;
+  if ((rc = sc_get_tensor_map(a->k, (uint64_t)a->H * HD, rows, a->k_rs, 64, TILE, &tk))) return rc;
+  if ((rc = sc_get_tensor_map(a->v, (uint64_t)a->H * HD, rows, a->v_rs, 64, TILE, &tv))) return rc;
+  if ((rc = sc_get_tensor_map(g->d_o, (uint64_t)a->H * HD, rows, a->o_rs, 64, TILE, &tdo))) return rc;
   sc_count_launch(2);
   const long n = rows * a->H;
   attn_delta_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>((const bf16*)a->o, (const bf16*)g->d_o, a->o_bs, a->o_rs, a->B,
