@@ -296,6 +296,15 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     int it = 0;
     for (int w = blockIdx.x; w + (int)gridDim.x < total; w += gridDim.x, ++it) {
       const int wn = w + gridDim.x;
+      {   // first touch of the next item goes to L2 now, a whole item ahead of the smem loads below
+        const int h = wn % a.H, b = wn / a.H;
+        for (int g = 0; g < ntile; ++g) {
+          tma_prefetch_2d_e(&tmQ, h * HD, b * L + g * TILE);
+          tma_prefetch_2d_e(&tmK, h * HD, b * L + g * TILE);
+          tma_prefetch_2d_e(&tmV, h * HD, b * L + g * TILE);
+          tma_prefetch_2d_e(&tmdO, h * HD, b * L + g * TILE);
+        }
+      }
       if (np > 1) {
         mbar_wait(bar_free0, it & 1);
         issue_group(wn, 0);
@@ -315,7 +324,19 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     bool first_pair = true;                             // very first pair of this CTA: no earlier MMAs read the tiles
     // this thread's two query rows (one per query tile): lse and delta straight from global (coalesced); the next
     // item's values are requested before the epilogues of the current one, so their latency is never exposed
-    float lse_c[2], dl_c[2], lse_n[2] = {0.f, 0.f}, dl_n[2] = {0.f, 0.f};
+    float lse_c[2], dl_c[2];
+    auto prefetch_rows = [&](int w) {                   // (registers are tight: holding the next item's values spilled them)
+      const int h = w % a.H, b = w / a.H;
+#pragma unroll
+      for (int t = 0; t < 2; ++t) {
+        const int qi = t * TILE + r;
+        const long o = ((long)b * a.H + h) * L + qi;
+        if (qi < L && (lane & 7) == 0) {                // one request per 32-byte sector
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(a.lse + o));
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(delta + o));
+        }
+      }
+    };
     auto load_rows = [&](int w, float (&ls)[2], float (&dl)[2]) {
       const int h = w % a.H, b = w / a.H;
 #pragma unroll
@@ -343,17 +364,15 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         store16_bf16((bf16*)gd.d_k + (long)b * a.k_bs + (long)key * a.k_rs + h * HD + cg * 16, kk, a.scale);
       }
     };
-    if ((int)blockIdx.x < total) load_rows(blockIdx.x, lse_c, dl_c);
     for (int w = blockIdx.x; w < total; w += gridDim.x) {
       const int h = w % a.H, b = w / a.H;
-      const float lse2v[2] = {lse_c[0] * LOG2E_F, lse_c[1] * LOG2E_F};
-      const float dlv[2] = {dl_c[0], dl_c[1]};
+      load_rows(w, lse_c, dl_c);                         // L2 hits (prefetched below); consumed after the wait for S
       for (int kt = 0; kt < ntile; ++kt) {
         const int q_first = CAUSAL ? kt : 0;
         for (int qt = q_first; qt < ntile; ++qt) {
           const int qi = qt * TILE + r;                    // this thread's query
           const int key0 = kt * TILE + cg * 32;            // first key of this warp's column group
-          const float lse2 = qt ? lse2v[1] : lse2v[0], dl = qt ? dlv[1] : dlv[0];
+          const float lse2 = (qt ? lse_c[1] : lse_c[0]) * LOG2E_F, dl = qt ? dl_c[1] : dl_c[0];
           if (warp == 0) TRACE(1, 10);
           mbar_wait(bar_s, ph_s);
           ph_s ^= 1;
@@ -420,7 +439,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
           }
         }
       }
-      if (w + (int)gridDim.x < total) load_rows(w + gridDim.x, lse_n, dl_n);
+      if (w + (int)gridDim.x < total) prefetch_rows(w + gridDim.x);
       dkv_epilogue(ntile - 1, h, b);
       if (warp == 0) TRACE(1, 16);
       // ---- dQ (TMEM lanes = queries): bar_dkv of the last key tile was committed after every MMA of the item
@@ -436,8 +455,6 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
           store16_bf16((bf16*)gd.d_q + (long)b * a.q_bs + (long)(TILE + r) * a.q_rs + h * HD + cg * 16, v1, a.scale);
         if (warp == 0) TRACE(1, 17);
       }
-      lse_c[0] = lse_n[0]; lse_c[1] = lse_n[1];
-      dl_c[0] = dl_n[0]; dl_c[1] = dl_n[1];
     }
   }
   tcgen05_fence_before();
@@ -506,16 +523,17 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   const int npad = (L + 15) & ~15;                 // MMA N of S, MMA K of P V
   const int total = ntile * a.H * a.B;
 
+  // (called by the whole control warp: one elected lane issues)
   auto issue_qk = [&](int w) {
     const int qt = w % ntile, h = (w / ntile) % a.H, b = w / (ntile * a.H);
-    mbar_expect_tx(bar_load, TILE * 128 + ntile * TILE * 128);
-    tma_load_2d(&tmQ, bar_load, smem + F_SM_Q, h * HD, b * L + qt * TILE);
-    tma_load_2d(&tmK, bar_load, smem + F_SM_K, h * HD, b * L);
+    mbar_expect_tx_e(bar_load, TILE * 128 + ntile * TILE * 128);
+    tma_load_2d_e(&tmQ, bar_load, smem + F_SM_Q, h * HD, b * L + qt * TILE);
+    tma_load_2d_e(&tmK, bar_load, smem + F_SM_K, h * HD, b * L);
   };
   auto issue_v = [&](int w) {
     const int h = (w / ntile) % a.H, b = w / (ntile * a.H);
-    mbar_expect_tx(bar_v, ntile * TILE * 128);
-    tma_load_2d(&tmV, bar_v, smem + F_SM_V, h * HD, b * L);
+    mbar_expect_tx_e(bar_v, ntile * TILE * 128);
+    tma_load_2d_e(&tmV, bar_v, smem + F_SM_V, h * HD, b * L);
   };
 
   if (threadIdx.x == 4 * 32) {
@@ -527,11 +545,11 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     mbar_init(bar_free, 4);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    issue_qk(blockIdx.x);
-    issue_v(blockIdx.x);
   }
   if (warp == 4) {
     __syncwarp();
+    issue_qk(blockIdx.x);
+    issue_v(blockIdx.x);
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(F_TM_COLS) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
@@ -541,7 +559,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   const uint32_t tmem = *tmem_slot;
 
   if (warp == 4) {
-    if (lane == 0) {
+    {   // warp-uniform control flow; single-lane instructions are elected inside the *_e wrappers
       const uint32_t id_s = make_idesc(npad, false, false);
       constexpr uint32_t ID_PV = make_idesc(64, false, true);
       uint32_t par = 0;
@@ -554,9 +572,9 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         for (int kk = 0; kk < 4; ++kk) {
           const uint64_t dq_ = desc_sw128(sbase + F_SM_Q + kk * 32, 16, 1024);
           const uint64_t dk_ = desc_sw128(sbase + F_SM_K + kk * 32, 16, 1024);
-          tcgen05_mma_f16(tmem, dq_, dk_, id_s, kk > 0);
+          tcgen05_mma_f16_e(tmem, dq_, dk_, id_s, kk > 0);
         }
-        tcgen05_commit(bar_s);
+        tcgen05_commit_e(bar_s);
         mbar_wait(bar_s, par);                       // Q / K consumed: the next item's may land
         if (wn < total) issue_qk(wn);
         mbar_wait(bar_v, par);
@@ -565,9 +583,9 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         const int nk = CAUSAL ? min(npad, ((qt * TILE + TILE + 15) & ~15)) >> 4 : npad >> 4;   // keys past the tile's last query: P = 0
         for (int kk = 0; kk < nk; ++kk) {
           const uint64_t dv_ = desc_sw128(sbase + F_SM_V + kk * 16 * 128, 8192, 1024);
-          tcgen05_mma_f16_ts(tmem + F_TM_O, tmem + kk * 8, dv_, ID_PV, kk > 0);
+          tcgen05_mma_f16_ts_e(tmem + F_TM_O, tmem + kk * 8, dv_, ID_PV, kk > 0);
         }
-        tcgen05_commit(bar_o);
+        tcgen05_commit_e(bar_o);
         mbar_wait(bar_o, par);                       // V consumed
         if (wn < total) issue_v(wn);
         mbar_wait(bar_free, par);                    // O read out: the accumulator columns may be overwritten

@@ -39,24 +39,32 @@ SC_DEVINL uint32_t cluster_ctarank() {
 SC_DEVINL void cluster_sync_all() {
   asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
+// (the *_e wrappers are called by a whole warp under uniform control flow; one elected lane executes -- see
+// tcgen05_mma_f16_e in gemm_tc_common.cuh)
 SC_DEVINL void tma_load_2d_2sm(const CUtensorMap* map, uint64_t* leader_bar, void* dst, int c0, int c1) {
   asm volatile(
-      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      "{\n\t.reg .pred e;\n\t"
+      "elect.sync _|e, 0xffffffff;\n\t"
+      "@e cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];\n\t}"
       ::"r"(smem_u32(dst)), "l"((uint64_t)map), "r"(smem_u32(leader_bar) & PEER_MASK), "r"(c0), "r"(c1)
       : "memory");
 }
 SC_DEVINL void tcgen05_mma2_f16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accum) {
   asm volatile(
-      "{\n\t.reg .pred p;\n\t"
+      "{\n\t.reg .pred p, e;\n\t"
+      "elect.sync _|e, 0xffffffff;\n\t"
       "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      "@e tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
       ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accum)
       : "memory");
 }
 SC_DEVINL void tcgen05_commit2(uint64_t* bar) {   // arrives on the same barrier of both CTAs
-  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
-               ::"r"(smem_u32(bar)), "h"((uint16_t)3)
-               : "memory");
+  asm volatile(
+      "{\n\t.reg .pred e;\n\t"
+      "elect.sync _|e, 0xffffffff;\n\t"
+      "@e tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;\n\t}"
+      ::"r"(smem_u32(bar)), "h"((uint16_t)3)
+      : "memory");
 }
 SC_DEVINL void mbar_arrive_leader(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(smem_u32(bar) & PEER_MASK) : "memory");
@@ -108,10 +116,13 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   const int num_items = tiles_m * tiles_n * splits;
 
   if (warp == EPI2_WARPS) {
-    // =============================== TMA producer (both CTAs) ===============================
-    if (lane == 0) {
-      asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tmA) : "memory");
-      asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tmB) : "memory");
+    // =============================== TMA producer (both CTAs; whole warp, elected issue) ===============================
+    {
+      if (lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tmA) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tmB) : "memory");
+      }
+      __syncwarp();
       int stage = 0;
       uint32_t phase = 0;
       for (int item = pair; item < num_items; item += npairs) {
@@ -124,7 +135,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         // (prefetching the next tile's operands into L2 from here was measured on B200: -15 % on the K = 768 shapes)
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
-          if (rank == 0) mbar_expect_tx(&full_bar[stage], 2 * STAGE2_BYTES);
+          if (rank == 0) mbar_expect_tx_e(&full_bar[stage], 2 * STAGE2_BYTES);
           uint8_t* sa = smem_a + stage * A2_BYTES;
           uint8_t* sb = smem_b + stage * B2_BYTES;
           if (!A_MN) {
@@ -144,8 +155,8 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       }
     }
   } else if (warp == EPI2_WARPS + 1) {
-    // =============================== MMA issuer (leader CTA only) ===============================
-    if (lane == 0 && rank == 0) {
+    // =============================== MMA issuer (leader CTA only; whole warp, elected issue) ===============================
+    if (rank == 0) {
       constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((A_MN ? 1u : 0u) << 15) | ((B_MN ? 1u : 0u) << 16) |
                                  ((uint32_t)(256 >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
       constexpr uint32_t a_kstep = A_MN ? (16 * 128) >> 4 : (16 * 2) >> 4;
