@@ -123,3 +123,51 @@ def test_colsum_vectorised_and_scalar():
         ops.colsum_op(x, out)()
         ref = x.float().sum(0)
         assert float((out - ref).abs().max()) < 1e-3 * (1 + float(ref.abs().max()))
+
+
+# ---- 2-CTA kernel (M >= 512, N >= 256): TMA-store epilogues, ragged edges clipped by the tensor map -----------------
+@pytest.mark.parametrize("M,N,K", [(1000, 3072, 768), (2048, 512, 512), (777, 1000, 256), (4100, 2304, 768)])
+def test_tc2_tma_store_epilogues(M, N, K):
+    _run(M, N, K, torch.bfloat16, c_dtype=torch.bfloat16)                                              # plain
+    _run(M, N, K, torch.bfloat16, bias=True, c_dtype=torch.bfloat16)                                   # + bias
+    _run(M, N, K, torch.bfloat16, bias=True, act=1, c_dtype=torch.bfloat16, c2=torch.bfloat16)         # QuickGELU, two outputs
+    _run(M, N, K, torch.bfloat16, bias=True, act=2, c_dtype=torch.bfloat16, c2=torch.bfloat16)         # erf-GELU, two outputs
+    _run(M, N, K, torch.bfloat16, tb=True, c_dtype=torch.bfloat16)                                     # dgrad layout
+    _run(M, N, K, torch.bfloat16, bias=True, residual=True)                                            # fp32 residual path
+
+
+def test_tc2_outputs_do_not_spill_past_the_edges():
+    """TMA boxes that overhang M or N must not write outside C (checked with a guard band around a strided C)."""
+    from segclip_b200 import ops
+    torch.manual_seed(0)
+    M, N, K, pad = 1000, 1000, 256, 8
+    A = torch.randn(M, K, device="cuda").bfloat16()
+    B = torch.randn(N, K, device="cuda").bfloat16()
+    big = torch.full((M + 40, N + pad), 7.0, device="cuda", dtype=torch.bfloat16)
+    C = big[:M, :N]
+    ops.gemm(A, B, C, bias=torch.zeros(N, device="cuda"))
+    torch.cuda.synchronize()
+    ref = A.float() @ B.float().t()
+    assert float((C.float() - ref).abs().max() / ref.abs().max()) < 1e-2
+    assert bool((big[M:] == 7.0).all()) and bool((big[:, N:] == 7.0).all())
+
+
+def test_tc2_fused_activation_backward_with_colsum():
+    """The activation-gradient dgrad of the 2-CTA kernel incl. the fused column sums (c_fc bias gradient)."""
+    from segclip_b200 import ops
+    torch.manual_seed(0)
+    for act in (1, 2):
+        M, N, K = 1576, 3072, 768
+        dy = torch.randn(M, K, device="cuda").bfloat16()
+        W = (torch.randn(K, N, device="cuda") * 0.05).bfloat16()
+        pre = torch.randn(M, N, device="cuda").bfloat16()
+        out = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
+        cs = torch.zeros(N, device="cuda")
+        ops.gemm(dy, W, out, trans_b=True, mul_aux=pre, mul_aux_act=act, colsum_out=cs)
+        torch.cuda.synchronize()
+        x = pre.float().requires_grad_(True)
+        y = x * torch.sigmoid(1.702 * x) if act == 1 else torch.nn.functional.gelu(x)
+        y.backward(dy.float() @ W.float())
+        assert float((out.float() - x.grad).abs().max() / x.grad.abs().max()) < 1e-2
+        ref = out.float().sum(0)
+        assert float((cs - ref).abs().max()) < 2e-3 * (1 + float(ref.abs().max()))
