@@ -231,7 +231,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   }
 
   if constexpr (EpiTma<EF>::value) {
-    if (warp < EPI2_WARPS && lane == 0) bulk_wait_all();     // staging smem must outlive the last TMA stores
+    if (warp < EPI2_WARPS) bulk_wait_all();                  // staging smem must outlive the last TMA stores
   }
   tcgen05_fence_before();
   cluster_sync_all();

@@ -387,14 +387,24 @@ SC_DEVINL void epi_finish(const EpiParams& ep, float (&v)[32], uint32_t stage, i
 // SWIZZLE_64B layout (conflict-free 16-byte stores) and handed to the TMA (cp.async.bulk.tensor store): no transposed
 // read-back, no per-lane global stores.  Four 2 KB boxes per warp rotate; a box is rewritten only after the bulk group
 // that read it has completed (cp.async.bulk.wait_group.read).
+// (whole warp calls these; the elected lane -- always the same one for a full mask -- owns the bulk groups)
 SC_DEVINL void tma_store_2d(const CUtensorMap* map, uint32_t src, int c0, int c1) {
-  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
-               ::"l"((uint64_t)map), "r"(src), "r"(c0), "r"(c1) : "memory");
+  asm volatile(
+      "{\n\t.reg .pred e;\n\t"
+      "elect.sync _|e, 0xffffffff;\n\t"
+      "@e cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];\n\t}"
+      ::"l"((uint64_t)map), "r"(src), "r"(c0), "r"(c1) : "memory");
 }
-SC_DEVINL void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+SC_DEVINL void bulk_commit() {
+  asm volatile("{\n\t.reg .pred e;\n\telect.sync _|e, 0xffffffff;\n\t@e cp.async.bulk.commit_group;\n\t}" ::: "memory");
+}
 template <int N>
-SC_DEVINL void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
-SC_DEVINL void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+SC_DEVINL void bulk_wait_read() {
+  asm volatile("{\n\t.reg .pred e;\n\telect.sync _|e, 0xffffffff;\n\t@e cp.async.bulk.wait_group.read %0;\n\t}" ::"n"(N) : "memory");
+}
+SC_DEVINL void bulk_wait_all() {
+  asm volatile("{\n\t.reg .pred e;\n\telect.sync _|e, 0xffffffff;\n\t@e cp.async.bulk.wait_group 0;\n\t}" ::: "memory");
+}
 
 template <int EF>
 struct EpiTma {
@@ -409,7 +419,7 @@ SC_DEVINL void epi_finish_tma(const EpiParams& ep, float (&v)[32], uint32_t stag
   constexpr bool two = EpiTma<EF>::two;
   const uint32_t buf_out = stage + ((two ? 2 * g + 1 : g) & 3u) * 2048u;
   const uint32_t buf_c2 = stage + ((2 * g) & 3u) * 2048u;
-  if (lane == 0) bulk_wait_read<two ? 1 : 3>();      // the group that last read these boxes has retired
+  bulk_wait_read<two ? 1 : 3>();                     // the group that last read these boxes has retired
   if constexpr ((EF & EF_BIAS) != 0) {
     // breg = the 4 bias values of columns 4*lane.. of this warp's 128-column range, loaded once per tile BEFORE the wait
     // for the accumulator (the L1 left beside 224 KB of smem is ~4 KB: a per-chunk __ldg exposed an L2 round trip per chunk
@@ -445,11 +455,11 @@ SC_DEVINL void epi_finish_tma(const EpiParams& ep, float (&v)[32], uint32_t stag
                                                                pack2_bf16(v[8 * j + 4], v[8 * j + 5]), pack2_bf16(v[8 * j + 6], v[8 * j + 7])));
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic-proxy writes -> visible to the TMA
   __syncwarp();
-  if (lane == 0 && n0 < ep.N && mrow0 < ep.M) {
+  if (n0 < ep.N && mrow0 < ep.M) {                   // warp-uniform
     if constexpr (two) tma_store_2d(tmC2, buf_c2, n0, mrow0);
     tma_store_2d(tmC, buf_out, n0, mrow0);
   }
-  if (lane == 0) bulk_commit();
+  bulk_commit();
 }
 
 // Shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout), SWIZZLE_128B.
