@@ -164,15 +164,19 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   // boxes: the first rows of Q/K/V/dO are last read by the second-to-last pair, so the next item's first group is
   // loaded under the last pair and only the second group waits for the item's final MMAs.
   // (called by the whole control warp: one elected lane issues)
-  auto issue_group = [&](int w, int g) {
+  // rg = row group of the item (rows rg*128 ..), buf = which 16 KB half of each operand buffer receives it
+  auto issue_group = [&](int w, int rg, int buf) {
     const int h = w % a.H, b = w / a.H;
-    uint64_t* bar = g ? bar_load1 : bar_load;
+    uint64_t* bar = buf ? bar_load1 : bar_load;
     mbar_expect_tx_e(bar, 4 * TILE * 128);
-    tma_load_2d_e(&tmQ, bar, smem + SM_Q + g * 16384, h * HD, b * L + g * TILE);
-    tma_load_2d_e(&tmK, bar, smem + SM_K + g * 16384, h * HD, b * L + g * TILE);
-    tma_load_2d_e(&tmV, bar, smem + SM_V + g * 16384, h * HD, b * L + g * TILE);
-    tma_load_2d_e(&tmdO, bar, smem + SM_DO + g * 16384, h * HD, b * L + g * TILE);
+    tma_load_2d_e(&tmQ, bar, smem + SM_Q + buf * 16384, h * HD, b * L + rg * TILE);
+    tma_load_2d_e(&tmK, bar, smem + SM_K + buf * 16384, h * HD, b * L + rg * TILE);
+    tma_load_2d_e(&tmV, bar, smem + SM_V + buf * 16384, h * HD, b * L + rg * TILE);
+    tma_load_2d_e(&tmdO, bar, smem + SM_DO + buf * 16384, h * HD, b * L + rg * TILE);
   };
+  // Single-tile items (L <= 128: text, MAE pass) use the two halves as a double buffer instead: item i lives in half
+  // i & 1, so the next item's operands land while this one computes.
+  const bool dbuf = ntile == 1;
   if (threadIdx.x == NSOFT * 32) {
     mbar_init(bar_load, 1);
     mbar_init(bar_load1, 1);
@@ -189,8 +193,9 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   }
   if (warp == NSOFT) {
     __syncwarp();
-    issue_group(blockIdx.x, 0);       // flies while TMEM is allocated
-    if (ntile > 1) issue_group(blockIdx.x, 1);
+    issue_group(blockIdx.x, 0, 0);    // flies while TMEM is allocated
+    if (ntile > 1) issue_group(blockIdx.x, 1, 1);
+    else if ((int)(blockIdx.x + gridDim.x) < total) issue_group(blockIdx.x + gridDim.x, 0, 1);
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
@@ -205,18 +210,19 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       constexpr uint32_t ID_S = make_idesc(128, false, false);   // S, dP : A K-major, B K-major
       constexpr uint32_t ID_TT = make_idesc(64, true, true);     // dV, dK: A = tile read MN-major, B MN-major
       constexpr uint32_t ID_NT = make_idesc(64, false, true);    // dQ    : A = tile K-major,       B MN-major
+      uint32_t ob = 0;                               // byte offset of the item's half (double-buffered single-tile items)
       auto issue_sdp = [&](int kt, int qt) {
         // S^T = K_kt Q_qt^T and dP^T = V_kt dO_qt^T (their TMEM columns were released by bar_p of the previous pair)
 #pragma unroll
         for (int kk = 0; kk < 4; ++kk) {
-          const uint64_t dq_ = desc_sw128(sbase + SM_Q + qt * 16384 + kk * 32, 16, 1024);
-          const uint64_t dk_ = desc_sw128(sbase + SM_K + kt * 16384 + kk * 32, 16, 1024);
+          const uint64_t dq_ = desc_sw128(sbase + SM_Q + ob + qt * 16384 + kk * 32, 16, 1024);
+          const uint64_t dk_ = desc_sw128(sbase + SM_K + ob + kt * 16384 + kk * 32, 16, 1024);
           tcgen05_mma_f16_e(tmem + TM_ST, dq_, dk_, ID_S, kk > 0);
         }
 #pragma unroll
         for (int kk = 0; kk < 4; ++kk) {
-          const uint64_t do_ = desc_sw128(sbase + SM_DO + qt * 16384 + kk * 32, 16, 1024);
-          const uint64_t dv_ = desc_sw128(sbase + SM_V + kt * 16384 + kk * 32, 16, 1024);
+          const uint64_t do_ = desc_sw128(sbase + SM_DO + ob + qt * 16384 + kk * 32, 16, 1024);
+          const uint64_t dv_ = desc_sw128(sbase + SM_V + ob + kt * 16384 + kk * 32, 16, 1024);
           tcgen05_mma_f16_e(tmem + TM_DPT, do_, dv_, ID_S, kk > 0);
         }
         tcgen05_commit_e(bar_s);
@@ -229,7 +235,12 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         int pi = 0;
         bool have1 = ntile == 1;                     // second operand group waited for
         TRACE(0, 1);
-        mbar_wait(bar_load, it & 1);
+        if (dbuf) {
+          ob = (it & 1) * 16384u;
+          mbar_wait((it & 1) ? bar_load1 : bar_load, (it >> 1) & 1);
+        } else {
+          mbar_wait(bar_load, it & 1);
+        }
         tcgen05_fence_after();
         TRACE(0, 2);
         issue_sdp(0, 0);
@@ -265,15 +276,15 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
               // tile [query rows][key cols] read as MN-major A: 64-key chunks 16 KB apart (LBO), 8-query groups 1 KB (SBO)
               const uint64_t dpa = desc_sw128(sbase + SM_PT + kq * 2048, 16384, 1024);
               const uint64_t dsa = desc_sw128(sbase + SM_DST + kq * 2048, 16384, 1024);
-              const uint64_t dob = desc_sw128(sbase + SM_DO + (qt * TILE + kq * 16) * 128, 8192, 1024);
-              const uint64_t dqb = desc_sw128(sbase + SM_Q + (qt * TILE + kq * 16) * 128, 8192, 1024);
+              const uint64_t dob = desc_sw128(sbase + SM_DO + ob + (qt * TILE + kq * 16) * 128, 8192, 1024);
+              const uint64_t dqb = desc_sw128(sbase + SM_Q + ob + (qt * TILE + kq * 16) * 128, 8192, 1024);
               tcgen05_mma_f16_e(tmem + TM_DV, dpa, dob, ID_TT, (qt > q_first || kq > 0));
               tcgen05_mma_f16_e(tmem + TM_DK, dsa, dqb, ID_TT, (qt > q_first || kq > 0));
             }
 #pragma unroll
             for (int kk = 0; kk < 8; ++kk) {           // contraction over the 128 keys of this tile (tile columns)
               const uint64_t dsa = desc_sw128(sbase + SM_DST + (kk >> 2) * 16384 + (kk & 3) * 32, 16, 1024);
-              const uint64_t dkb = desc_sw128(sbase + SM_K + (kt * TILE + kk * 16) * 128, 8192, 1024);
+              const uint64_t dkb = desc_sw128(sbase + SM_K + ob + (kt * TILE + kk * 16) * 128, 8192, 1024);
               tcgen05_mma_f16_e(tmem + TM_DQ + qt * 64, dsa, dkb, ID_NT, (kt > 0 || kk > 0));
             }
             tcgen05_commit_e(bar_done);
@@ -285,7 +296,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
           }
           tcgen05_commit_e(bar_dkv);
         }
-        tcgen05_commit_e(bar_free1);
+        tcgen05_commit_e((dbuf && !(it & 1)) ? bar_free0 : bar_free1);
         TRACE(0, 7);
       }
     }
@@ -296,7 +307,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     int it = 0;
     for (int w = blockIdx.x; w + (int)gridDim.x < total; w += gridDim.x, ++it) {
       const int wn = w + gridDim.x;
-      {   // first touch of the next item goes to L2 now, a whole item ahead of the smem loads below
+      if (!dbuf) {   // first touch of the next item goes to L2 now, a whole item ahead of the smem loads below
         const int h = wn % a.H, b = wn / a.H;
         for (int g = 0; g < ntile; ++g) {
           tma_prefetch_2d_e(&tmQ, h * HD, b * L + g * TILE);
@@ -307,12 +318,13 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       }
       if (np > 1) {
         mbar_wait(bar_free0, it & 1);
-        issue_group(wn, 0);
+        issue_group(wn, 0, 0);
         mbar_wait(bar_free1, it & 1);
-        issue_group(wn, 1);
-      } else {
-        mbar_wait(bar_free1, it & 1);
-        issue_group(wn, 0);
+        issue_group(wn, 1, 1);
+      } else if (wn + (int)gridDim.x < total) {
+        // double buffer: item it+2 goes where item `it` lives, once item `it` has retired (item it+1 was loaded earlier)
+        mbar_wait((it & 1) ? bar_free1 : bar_free0, (it >> 1) & 1);
+        issue_group(wn + gridDim.x, 0, it & 1);
       }
     }
   } else {
@@ -364,6 +376,22 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         store16_bf16((bf16*)gd.d_k + (long)b * a.k_bs + (long)key * a.k_rs + h * HD + cg * 16, kk, a.scale);
       }
     };
+    auto dq_epilogue = [&](int h, int b) {
+      // dQ (TMEM lanes = queries): bar_dkv of the item's last key tile was committed after every MMA of the item
+      float v0[16], v1[16];
+      tmem_ld16(tmem + lane_off + TM_DQ + cg * 16, v0);
+      if (ntile > 1) tmem_ld16(tmem + lane_off + TM_DQ + 64 + cg * 16, v1);
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_dq_free);
+      if (r < L) store16_bf16((bf16*)gd.d_q + (long)b * a.q_bs + (long)r * a.q_rs + h * HD + cg * 16, v0, a.scale);
+      if (ntile > 1 && TILE + r < L)
+        store16_bf16((bf16*)gd.d_q + (long)b * a.q_bs + (long)(TILE + r) * a.q_rs + h * HD + cg * 16, v1, a.scale);
+    };
+    // The read-out of an item's last dV / dK and of its dQ is deferred until this warp has delivered the first tile of
+    // the NEXT item, so the MMA pipe never waits for the drain (the control warp holds the next item's accumulating
+    // MMAs back until bar_dkv_free / bar_dq_free).
+    int prev_h = -1, prev_b = 0;
     for (int w = blockIdx.x; w < total; w += gridDim.x) {
       const int h = w % a.H, b = w / a.H;
       load_rows(w, lse_c, dl_c);                         // L2 hits (prefetched below); consumed after the wait for S
@@ -436,25 +464,20 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
           if (qt == q_first && kt > 0) {
             dkv_epilogue(kt - 1, h, b);
             if (warp == 0) TRACE(1, 16);
+          } else if (qt == q_first && prev_h >= 0) {
+            dkv_epilogue(ntile - 1, prev_h, prev_b);
+            dq_epilogue(prev_h, prev_b);
+            if (warp == 0) TRACE(1, 17);
           }
         }
       }
       if (w + (int)gridDim.x < total) prefetch_rows(w + gridDim.x);
-      dkv_epilogue(ntile - 1, h, b);
-      if (warp == 0) TRACE(1, 16);
-      // ---- dQ (TMEM lanes = queries): bar_dkv of the last key tile was committed after every MMA of the item
-      {
-        float v0[16], v1[16];
-        tmem_ld16(tmem + lane_off + TM_DQ + cg * 16, v0);
-        if (ntile > 1) tmem_ld16(tmem + lane_off + TM_DQ + 64 + cg * 16, v1);
-        tcgen05_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(bar_dq_free);
-        if (r < L) store16_bf16((bf16*)gd.d_q + (long)b * a.q_bs + (long)r * a.q_rs + h * HD + cg * 16, v0, a.scale);
-        if (ntile > 1 && TILE + r < L)
-          store16_bf16((bf16*)gd.d_q + (long)b * a.q_bs + (long)(TILE + r) * a.q_rs + h * HD + cg * 16, v1, a.scale);
-        if (warp == 0) TRACE(1, 17);
-      }
+      prev_h = h;
+      prev_b = b;
+    }
+    if (prev_h >= 0) {
+      dkv_epilogue(ntile - 1, prev_h, prev_b);
+      dq_epilogue(prev_h, prev_b);
     }
   }
   tcgen05_fence_before();

@@ -53,6 +53,14 @@ def test_tensor_core_attention(B, H, L, hd, causal):
     _run(B, H, L, hd, torch.bfloat16, causal)
 
 
+@pytest.mark.parametrize("B,H,L,hd,causal", [(40, 12, 196, 64, False), (64, 8, 77, 64, True), (48, 8, 130, 64, True),
+                                             (80, 4, 48, 64, False), (37, 12, 256, 64, False)])
+def test_persistent_kernels_many_items_per_cta(B, H, L, hd, causal):
+    """More (sample, head) items than resident CTAs: exercises the persistent loops of the tcgen05 kernels -- operand
+    reloads, double-buffered single-tile items, deferred epilogues, barrier phase tracking across items."""
+    _run(B, H, L, hd, torch.bfloat16, causal, seed=3)
+
+
 @pytest.mark.parametrize("B,H,L,hd,causal", [(2, 3, 50, 64, False), (2, 2, 33, 48, True), (2, 2, 8, 8, False)])
 def test_generic_fp32_attention(B, H, L, hd, causal):
     _run(B, H, L, hd, torch.float32, causal)
