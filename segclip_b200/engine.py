@@ -156,7 +156,7 @@ class Engine:
         self.grads = {n: self.gflat[o:o + s].view(self.params[n].shape) for n, o, s in zip(names, offs, sizes)}
 
     # ------------------------------------------------------------------ native gradient all-reduce
-    def enable_grad_sync(self, group, bucket_mb=48):
+    def enable_grad_sync(self, group, bucket_mb=None):
         """Bucketed NCCL all-reduce of the flat gradient buffer, launched from inside the backward tape as soon as a
         prefix of the buffer is final (replaces DDP's hooks, main_task_align.py:251-252: the native backward is a single
         autograd node, so DDP could only reduce after it).  The mean (1/world) is folded into the final hand-over."""
@@ -173,7 +173,8 @@ class Engine:
         self._grad_last_op = last
         self._layout_grads(order)
         # buckets over the new order
-        limit = bucket_mb * (1 << 20) // 4
+        bucket_mb = bucket_mb or float(os.environ.get("SEGCLIP_BUCKET_MB", "48"))
+        limit = int(bucket_mb * (1 << 20)) // 4
         self.buckets = []          # (start, end, name of last param)
         start = 0
         for n in order:
