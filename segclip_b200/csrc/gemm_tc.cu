@@ -359,11 +359,7 @@ int sc_gemm_tc(const sc_gemm_desc* d, cudaStream_t st) {
 
   const int kb_total = ceil_div(d->K, BK);
   int splits = d->split_k;
-  if (splits < 0) {  // auto: fill roughly two waves of CTAs
-    const int tiles = ceil_div(d->M, BM) * ceil_div(d->N, BN);
-    splits = (2 * sc_num_sms() + tiles - 1) / tiles;
-    if (splits > kb_total / 4) splits = kb_total / 4;
-  }
+  if (splits < 0) splits = sc_pick_splits(ceil_div(d->M, BM) * ceil_div(d->N, BN), kb_total, sc_num_sms());
   if (splits < 1) splits = 1;
   if (splits > kb_total) splits = kb_total;
   if (splits > 1 && !(d->accumulate && d->c_dtype == SC_F32 && !d->C2)) {

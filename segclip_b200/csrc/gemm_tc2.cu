@@ -286,11 +286,7 @@ int sc_gemm_tc2(const sc_gemm_desc* d, cudaStream_t st) {
   if (waste * 8 > d->N) return SC_ERR_UNSUPPORTED;       // > 12.5 % padded columns: 128-wide tiles fit better
   const int kb_total = ceil_div(d->K, BK);
   int splits = d->split_k;
-  if (splits < 0) {
-    const int tiles = ceil_div(d->M, 256) * ceil_div(d->N, 256);
-    splits = (2 * (sc_num_sms() / 2) + tiles - 1) / tiles;
-    if (splits > kb_total / 4) splits = kb_total / 4;
-  }
+  if (splits < 0) splits = sc_pick_splits(ceil_div(d->M, 256) * ceil_div(d->N, 256), kb_total, sc_num_sms() / 2);
   if (splits < 1) splits = 1;
   if (splits > kb_total) splits = kb_total;
   if (splits > 1 && !(d->accumulate && d->c_dtype == SC_F32 && !d->C2)) {

@@ -480,6 +480,26 @@ SC_DEVINL uint64_t make_smem_desc(uint32_t smem_addr) {
 
 }  // namespace tc
 
+// Split-K factor for a persistent kernel with `workers` CTAs (or CTA pairs): every work item is one (tile, split) of
+// kb_per k-blocks and the workers take items round-robin, so the run lasts waves * (kb_per + per-item overhead).  The old
+// rule (fill two waves) left the last wave 20-55 % empty on the ViT-B wgrads (e.g. 36 tiles x 5 splits = 180 items on 74
+// pairs = 3 waves for 2.4 waves of work); this picks the split count with the lowest modelled time, fewest splits on ties.
+static inline int sc_pick_splits(int tiles, int kb_total, int workers) {
+  int best = 1;
+  long best_cost = -1;
+  int smax = kb_total / 4 < 64 ? kb_total / 4 : 64;
+  if (smax < 1) smax = 1;
+  for (int s = 1; s <= smax; ++s) {
+    const int kb_per = (kb_total + s - 1) / s;
+    if ((kb_total + kb_per - 1) / kb_per != s) continue;      // same launch as a smaller s
+    const long items = (long)tiles * s;
+    const long waves = (items + workers - 1) / workers;
+    const long cost = waves * (kb_per + 3);                    // ~3 k-blocks of prologue / atomic epilogue per item
+    if (best_cost < 0 || cost < best_cost) { best_cost = cost; best = s; }
+  }
+  return best;
+}
+
 // host helpers (gemm_tc.cu)
 int sc_get_tensor_map(const void* ptr, uint64_t dim0, uint64_t dim1, uint64_t stride_elems, uint32_t box0, uint32_t box1,
                       CUtensorMap* out);
