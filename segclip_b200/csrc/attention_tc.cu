@@ -503,9 +503,21 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
 //   epilogue: O / rowsum -> bf16 -> global; lse = m scale + ln(rowsum)
 // Warps 0-3: softmax + epilogue (TMEM lane quarter = warp); warp 4: TMA + MMA issue (one thread).
 constexpr int F_SM_Q = 0, F_SM_K = TILE * 128, F_SM_V = F_SM_K + OPER_BYTES;
+#ifndef SC_ATT_FWD_SOFT_WARPS
+#define SC_ATT_FWD_SOFT_WARPS 4
+#endif
+// Optional 8-softmax-warp variant (-DSC_ATT_FWD_SOFT_WARPS=8): two warps per TMEM lane quarter, each taking half of the
+// row's 32-column chunks (the 4-warp version runs at 2.4 warps per scheduler: issue slots 29 % busy, MUFU 33 %).
+// Measured on B200: correct (same tests) but SLOWER, 0.165 vs 0.134 ms per vision layer -- the two named barriers, the
+// smem detour and the lost TMEM-load prefetch cost more than the extra warps hide -- so 4 warps stay the default.
+// The halves exchange row max / row sum through smem and a 64-thread named barrier; the upper half parks its packed P in shared memory until the lower half has read all of its S
+// columns, because P (half as wide as S) lands on the lower half's columns.
+constexpr int F_NSOFT = SC_ATT_FWD_SOFT_WARPS;          // 4 or 8
 constexpr int F_SM_BAR = F_SM_V + OPER_BYTES;
-constexpr int F_SMEM_TOTAL = F_SM_BAR + 64;
-constexpr int F_THREADS = 5 * 32;
+constexpr int F_SM_X = F_SM_BAR + 64;                   // float [2 (max | sum)][2 (half)][128 rows]
+constexpr int F_SM_P = F_SM_X + 2 * 2 * 128 * 4;        // parked P of the upper half: [3 chunks][128 rows][64 B], XOR-swizzled
+constexpr int F_SMEM_TOTAL = F_SM_P + (F_NSOFT == 8 ? 3 * 128 * 64 : 0);
+constexpr int F_THREADS = (F_NSOFT + 1) * 32;
 constexpr uint32_t F_TM_O = 128, F_TM_COLS = 256;
 
 SC_DEVINL void tcgen05_mma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc, uint32_t accum) {
@@ -559,17 +571,17 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     tma_load_2d_e(&tmV, bar_v, smem + F_SM_V, h * HD, b * L);
   };
 
-  if (threadIdx.x == 4 * 32) {
+  if (threadIdx.x == F_NSOFT * 32) {
     mbar_init(bar_load, 1);
     mbar_init(bar_s, 1);
-    mbar_init(bar_p, 4);
+    mbar_init(bar_p, F_NSOFT);
     mbar_init(bar_o, 1);
     mbar_init(bar_v, 1);
-    mbar_init(bar_free, 4);
+    mbar_init(bar_free, F_NSOFT);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
-  if (warp == 4) {
+  if (warp == F_NSOFT) {
     __syncwarp();
     issue_qk(blockIdx.x);
     issue_v(blockIdx.x);
@@ -581,7 +593,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   tcgen05_fence_after();
   const uint32_t tmem = *tmem_slot;
 
-  if (warp == 4) {
+  if (warp == F_NSOFT) {
     {   // warp-uniform control flow; single-lane instructions are elected inside the *_e wrappers
       const uint32_t id_s = make_idesc(npad, false, false);
       constexpr uint32_t ID_PV = make_idesc(64, false, true);
@@ -616,10 +628,124 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       }
     }
   } else {
-    const uint32_t lane_off = (uint32_t)(warp * 32) << 16;
-    const int r = warp * 32 + lane;
+    const int quarter = warp & 3, half = warp >> 2;       // half is always 0 with 4 softmax warps
+    const uint32_t lane_off = (uint32_t)(quarter * 32) << 16;
+    const int r = quarter * 32 + lane;
     const float c = a.scale * LOG2E_F;
+    float* xs = (float*)(smem + F_SM_X);
     uint32_t par = 0;
+    if constexpr (F_NSOFT == 8) {
+      const int nchunks = (npad + 31) >> 5;
+      const int n1 = nchunks / 2 < 3 ? nchunks / 2 : 3;      // chunks of the upper half (its P waits in 24 KB of smem)
+      const int c_lo = half ? nchunks - n1 : 0, c_hi = half ? nchunks : nchunks - n1;
+      for (int w = blockIdx.x; w < total; w += gridDim.x, par ^= 1) {
+        const int qt = w % ntile, h = (w / ntile) % a.H, b = w / (ntile * a.H);
+        const int qi = qt * TILE + r;
+        const bool warp_live = qt * TILE + quarter * 32 < L;   // same for both warps of the quarter
+        float m = -INFINITY, sum = 0.f;
+        mbar_wait(bar_s, par);
+        tcgen05_fence_after();
+        if (warp_live) {
+          const int kmax = CAUSAL ? min(L, qi + 1) : L;
+          float s[32];
+          // ---- pass 1: max over this warp's chunks, then the row max across the two halves
+          float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+          for (int ch = c_lo; ch < c_hi; ++ch) {
+            const int c0 = ch * 32;
+            tmem_ld32_nowait(tmem + lane_off + c0, s);
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            if (c0 + 32 <= kmax) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) m4[j & 3] = fmaxf(m4[j & 3], s[j]);
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) m4[j & 3] = fmaxf(m4[j & 3], c0 + j < kmax ? s[j] : -INFINITY);
+            }
+          }
+          m = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
+          xs[half * 128 + r] = m;
+          asm volatile("bar.sync %0, 64;" ::"r"(1 + quarter) : "memory");
+          m = fmaxf(m, xs[(half ^ 1) * 128 + r]);
+          const float mc = (m == -INFINITY) ? 0.f : m * c;
+          // ---- pass 2: p, partial row sum; the lower half stores P at once (its P columns lie inside its own, already
+          // consumed S columns), the upper half parks it in shared memory
+          float s4[4] = {0.f, 0.f, 0.f, 0.f};
+          const uint32_t prow = sbase + F_SM_P + r * 64;
+          const int psw = (r >> 1) & 3;
+          for (int ch = c_lo; ch < c_hi; ++ch) {
+            const int i = ch - c_lo;
+            {
+              const int c0 = ch * 32;
+              tmem_ld32_nowait(tmem + lane_off + c0, s);
+              asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+              uint32_t q[16];
+              if (c0 + 32 <= kmax) {
+#pragma unroll
+                for (int j = 0; j < 32; j += 2) {
+                  const float p0 = ex2f(fmaf(s[j], c, -mc)), p1 = ex2f(fmaf(s[j + 1], c, -mc));
+                  s4[(j >> 1) & 3] += p0 + p1;
+                  q[j >> 1] = pack_bf16(p0, p1);
+                }
+              } else {
+#pragma unroll
+                for (int j = 0; j < 32; j += 2) {
+                  const float p0 = c0 + j < kmax ? ex2f(fmaf(s[j], c, -mc)) : 0.f;
+                  const float p1 = c0 + j + 1 < kmax ? ex2f(fmaf(s[j + 1], c, -mc)) : 0.f;
+                  s4[(j >> 1) & 3] += p0 + p1;
+                  q[j >> 1] = pack_bf16(p0, p1);
+                }
+              }
+              if (half == 0) {
+                tmem_st16(tmem + lane_off + (c0 >> 1), q);
+              } else {
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                  sts128u(prow + i * 8192 + ((j ^ psw) << 4), q[4 * j], q[4 * j + 1], q[4 * j + 2], q[4 * j + 3]);
+              }
+            }
+          }
+          sum = (s4[0] + s4[1]) + (s4[2] + s4[3]);
+          xs[256 + half * 128 + r] = sum;
+          asm volatile("bar.sync %0, 64;" ::"r"(1 + quarter) : "memory");   // lower half has read all of its S; sums visible
+          sum += xs[256 + (half ^ 1) * 128 + r];
+          if (half == 1) {
+#pragma unroll
+            for (int i = 0; i < 3; ++i) {
+              if (i < n1) {
+                uint32_t q[16];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  const uint4 u = lds128b(prow + i * 8192 + ((j ^ psw) << 4));
+                  q[4 * j] = u.x; q[4 * j + 1] = u.y; q[4 * j + 2] = u.z; q[4 * j + 3] = u.w;
+                }
+                tmem_st16(tmem + lane_off + ((c_lo + i) * 16), q);
+              }
+            }
+          }
+          asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+        }
+        tcgen05_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_p);
+        mbar_wait(bar_o, par);
+        tcgen05_fence_after();
+        float o[32];
+        if (warp_live) {
+          tmem_ld32_nowait(tmem + lane_off + F_TM_O + half * 32, o);
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        }
+        tcgen05_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_free);
+        if (warp_live && qi < L) {
+          const float inv = 1.0f / sum;
+          bf16* dst = (bf16*)a.o + (long)b * a.o_bs + (long)qi * a.o_rs + h * HD + half * 32;
+          store16_bf16(dst, o, inv);
+          store16_bf16(dst + 16, o + 16, inv);
+          if (half == 0) a.lse[((long)b * a.H + h) * L + qi] = m * a.scale + logf(sum);
+        }
+      }
+    } else
     for (int w = blockIdx.x; w < total; w += gridDim.x, par ^= 1) {
     const int qt = w % ntile, h = (w / ntile) % a.H, b = w / (ntile * a.H);
     const int qi = qt * TILE + r;
@@ -710,7 +836,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   }
   tcgen05_fence_before();
   __syncthreads();
-  if (warp == 4) {
+  if (warp == F_NSOFT) {
     tcgen05_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(F_TM_COLS) : "memory");
   }
