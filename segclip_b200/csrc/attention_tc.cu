@@ -230,7 +230,6 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       uint32_t ph_p = 0, ph_free = 0, ph_dq = 0;
       int it = 0;
       for (int w = blockIdx.x; w < total; w += gridDim.x, ++it) {
-        const int wn = w + gridDim.x;
         const int np = CAUSAL ? ntile * (ntile + 1) / 2 : ntile * ntile;   // pairs of this item
         int pi = 0;
         bool have1 = ntile == 1;                     // second operand group waited for
@@ -520,14 +519,6 @@ constexpr int F_SMEM_TOTAL = F_SM_P + (F_NSOFT == 8 ? 3 * 128 * 64 : 0);
 constexpr int F_THREADS = (F_NSOFT + 1) * 32;
 constexpr uint32_t F_TM_O = 128, F_TM_COLS = 256;
 
-SC_DEVINL void tcgen05_mma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc, uint32_t accum) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
-      ::"r"(tmem_d), "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accum)
-      : "memory");
-}
 SC_DEVINL void tmem_st16(uint32_t taddr, const uint32_t* r) {
   asm volatile(
       "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
@@ -857,7 +848,7 @@ bool sc_attn_tc_supported(const sc_attn_desc* a) {
 
 int sc_attention_bwd_tc(const sc_attn_bwd_desc* g, float* delta, cudaStream_t st) {
   const sc_attn_desc* a = &g->fwd;
-  const int L = a->Lq, ntile = (L + TILE - 1) / TILE;
+  const int L = a->Lq;
   const long rows = (long)a->B * L;
   CUtensorMap tq, tk, tv, tdo;
   int rc;
