@@ -109,13 +109,18 @@ int sc_get_tensor_map_sw(const void* ptr, uint64_t dim0, uint64_t dim1, uint64_t
 int sc_select_epilogue(const sc_gemm_desc* d, int splits) {
   using namespace tc;
   int ef = EF_GENERIC;
-  const bool simple = d->alpha == 1.0f && !d->rowbias && (!d->accumulate || splits > 1);
+  const bool simple = d->alpha == 1.0f && !d->rowbias;
+  const bool acc = d->accumulate && splits <= 1;
   // colsum_out is implemented by the bf16-output epilogues only (checked by the caller below)
   if (simple) {
     const bool bias = d->bias != nullptr, resid = d->residual != nullptr, c2 = d->C2 != nullptr, aux = d->mul_aux != nullptr;
     const bool out_bf16 = d->c_dtype == SC_BF16;
     if (splits > 1) {
       if (!bias && !resid && !c2 && !aux && d->act == SC_ACT_NONE) ef = EF_ATOMIC | EF_OUT_F32;
+    } else if (!aux && !c2 && !resid && !bias && d->act == SC_ACT_NONE && !out_bf16) {
+      ef = EF_OUT_F32 | (acc ? EF_ACCUM : 0);      // plain fp32 output (grouped-conv features, accumulated dgrads)
+    } else if (acc) {
+      // every other accumulating combination: generic epilogue
     } else if (!aux && !c2 && !resid && d->act == SC_ACT_NONE && out_bf16) {
       ef = bias ? EF_BIAS : 0;
     } else if (bias && c2 && d->c2_dtype == SC_BF16 && out_bf16 && d->act == SC_ACT_QUICKGELU && !resid && !aux) {
@@ -390,12 +395,15 @@ int sc_gemm_tc(const sc_gemm_desc* d, cudaStream_t st) {
     if (ef == (EF_BIAS | EF_QGELU | EF_C2)) SC_L(BN_, false, false, EF_BIAS | EF_QGELU | EF_C2) \
     if (ef == (EF_BIAS | EF_RESID | EF_OUT_F32)) SC_L(BN_, false, false, EF_BIAS | EF_RESID | EF_OUT_F32) \
     if (ef == (EF_BIAS | EF_GELU | EF_C2)) SC_L(BN_, false, false, EF_BIAS | EF_GELU | EF_C2)  \
+    if (ef == EF_OUT_F32) SC_L(BN_, false, false, EF_OUT_F32)                                \
     SC_L(BN_, false, false, EF_GENERIC)                                                      \
   }                                                                                          \
   if (!a_mn && b_mn) {                                                                       \
     if (ef == 0) SC_L(BN_, false, true, 0)                                                   \
     if (ef == EF_MULAUX_QGELU) SC_L(BN_, false, true, EF_MULAUX_QGELU)                       \
     if (ef == EF_MULAUX_GELU) SC_L(BN_, false, true, EF_MULAUX_GELU)                         \
+    if (ef == EF_OUT_F32) SC_L(BN_, false, true, EF_OUT_F32)                                 \
+    if (ef == (EF_OUT_F32 | EF_ACCUM)) SC_L(BN_, false, true, EF_OUT_F32 | EF_ACCUM)         \
     SC_L(BN_, false, true, EF_GENERIC)                                                       \
   }                                                                                          \
   if (a_mn && b_mn) {                                                                        \

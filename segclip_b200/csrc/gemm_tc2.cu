@@ -314,12 +314,15 @@ int sc_gemm_tc2(const sc_gemm_desc* d, cudaStream_t st) {
     if (ef == (EF_BIAS | EF_QGELU | EF_C2)) SC_L2(false, false, EF_BIAS | EF_QGELU | EF_C2)
     if (ef == (EF_BIAS | EF_RESID | EF_OUT_F32)) SC_L2(false, false, EF_BIAS | EF_RESID | EF_OUT_F32)
     if (ef == (EF_BIAS | EF_GELU | EF_C2)) SC_L2(false, false, EF_BIAS | EF_GELU | EF_C2)
+    if (ef == EF_OUT_F32) SC_L2(false, false, EF_OUT_F32)
     SC_L2(false, false, EF_GENERIC)
   }
   if (!a_mn && b_mn) {
     if (ef == 0) SC_L2(false, true, 0)
     if (ef == EF_MULAUX_QGELU) SC_L2(false, true, EF_MULAUX_QGELU)
     if (ef == EF_MULAUX_GELU) SC_L2(false, true, EF_MULAUX_GELU)
+    if (ef == EF_OUT_F32) SC_L2(false, true, EF_OUT_F32)
+    if (ef == (EF_OUT_F32 | EF_ACCUM)) SC_L2(false, true, EF_OUT_F32 | EF_ACCUM)
     SC_L2(false, true, EF_GENERIC)
   }
   if (ef == (EF_ATOMIC | EF_OUT_F32)) SC_L2(true, true, EF_ATOMIC | EF_OUT_F32)

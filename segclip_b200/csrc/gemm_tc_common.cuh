@@ -146,6 +146,7 @@ enum : int {
   EF_ATOMIC = 64,       // split-K: atomic accumulate into fp32 C
   EF_GELU = 128,        // exact erf GELU (MAE decoder / proj_o MLP)
   EF_MULAUX_GELU = 256, // * GELU'(aux)
+  EF_ACCUM = 512,       // C += result (fp32 read-modify-write, single split; old C prefetched like a residual)
   EF_GENERIC = 1 << 20
 };
 
@@ -200,8 +201,8 @@ SC_DEVINL void epi4_fast(const EpiParams& p, int m, int n, float4 v, const float
       v.x *= act_grad(a.x, SC_ACT_GELU_ERF); v.y *= act_grad(a.y, SC_ACT_GELU_ERF);
       v.z *= act_grad(b.x, SC_ACT_GELU_ERF); v.w *= act_grad(b.y, SC_ACT_GELU_ERF);
     }
-    if constexpr ((F & EF_RESID) != 0) {
-      v.x += pre.x; v.y += pre.y; v.z += pre.z; v.w += pre.w;    // prefetched residual
+    if constexpr ((F & (EF_RESID | EF_ACCUM)) != 0) {
+      v.x += pre.x; v.y += pre.y; v.z += pre.z; v.w += pre.w;    // prefetched residual / old C
     }
     if constexpr ((F & EF_ATOMIC) != 0) {
       // one 16-byte vector reduction instead of four scalar atomics (split-K wgrad: fp32 accumulate in L2)
@@ -265,6 +266,9 @@ SC_DEVINL void epi_prefetch(const EpiParams& ep, int lane, int mrow0, int n0, fl
         pre[i] = make_float4(0.f, 0.f, 0.f, 0.f);
         if constexpr (EF != EF_GENERIC && (EF & EF_RESID) != 0) {
           if (m < ep.M) pre[i] = *(const float4*)(ep.residual + (long)m * ep.ldr + n);
+        }
+        if constexpr (EF != EF_GENERIC && (EF & EF_ACCUM) != 0) {
+          if (m < ep.M) pre[i] = *(const float4*)((const float*)ep.C + (long)m * ep.ldc + n);
         }
       }
     }

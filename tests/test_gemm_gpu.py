@@ -171,3 +171,12 @@ def test_tc2_fused_activation_backward_with_colsum():
         assert float((out.float() - x.grad).abs().max() / x.grad.abs().max()) < 1e-2
         ref = out.float().sum(0)
         assert float((cs - ref).abs().max()) < 2e-3 * (1 + float(ref.abs().max()))
+
+
+@pytest.mark.parametrize("M,N,K", [(392, 768, 768), (1000, 768, 768), (4100, 768, 1536)])
+def test_tc_plain_fp32_output_and_accumulate(M, N, K):
+    """Specialised fp32-output epilogues of both tcgen05 kernels: plain store and non-atomic C += (alpha = 1)."""
+    _run(M, N, K, torch.bfloat16)                                   # NN, fp32 out
+    _run(M, N, K, torch.bfloat16, tb=True)                          # NT, fp32 out
+    _run(M, N, K, torch.bfloat16, tb=True, accumulate=True)         # NT, C += (old C prefetched)
+    _run(M, N, K, torch.bfloat16, accumulate=True)                  # NN accumulate: generic path
