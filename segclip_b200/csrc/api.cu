@@ -18,12 +18,13 @@ void sc_set_error(const char* fmt, ...) {
 void sc_count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
 int sc_num_sms() {
-  static int n = 0;
+  static std::atomic<int> cache[64];
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+  int n = cache[dev & 63].load(std::memory_order_relaxed);
   if (n == 0) {
-    int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess ||
-        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
-      n = 148;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    cache[dev & 63].store(n, std::memory_order_relaxed);
   }
   return n;
 }

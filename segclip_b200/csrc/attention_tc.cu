@@ -864,12 +864,12 @@ int sc_attention_bwd_tc(const sc_attn_bwd_desc* g, float* delta, cudaStream_t st
   const long items = (long)a->H * a->B;
   dim3 grid((unsigned)(items < sc_num_sms() ? items : sc_num_sms()));       // persistent: one CTA per SM
   if (a->causal) {
-    static bool cfg = false;
-    if (!cfg) { SC_CUDA(cudaFuncSetAttribute(attn_bwd_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL)); cfg = true; }
+    static sc_device_once once;
+    if (once.first()) { SC_CUDA(cudaFuncSetAttribute(attn_bwd_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL)); once.done(); }
     attn_bwd_tc_kernel<true><<<grid, TC_THREADS, SMEM_TOTAL, st>>>(tq, tk, tv, tdo, *g, delta);
   } else {
-    static bool cfg = false;
-    if (!cfg) { SC_CUDA(cudaFuncSetAttribute(attn_bwd_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL)); cfg = true; }
+    static sc_device_once once;
+    if (once.first()) { SC_CUDA(cudaFuncSetAttribute(attn_bwd_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL)); once.done(); }
     attn_bwd_tc_kernel<false><<<grid, TC_THREADS, SMEM_TOTAL, st>>>(tq, tk, tv, tdo, *g, delta);
   }
   SC_LAUNCH_CHECK();
@@ -889,12 +889,12 @@ int sc_attention_fwd_tc(const sc_attn_desc* a, cudaStream_t st) {
   const long slots = 2L * sc_num_sms();
   dim3 grid((unsigned)(total < slots ? total : slots));
   if (a->causal) {
-    static bool cfg = false;
-    if (!cfg) { SC_CUDA(cudaFuncSetAttribute(attn_fwd_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, F_SMEM_TOTAL)); cfg = true; }
+    static sc_device_once once;
+    if (once.first()) { SC_CUDA(cudaFuncSetAttribute(attn_fwd_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, F_SMEM_TOTAL)); once.done(); }
     attn_fwd_tc_kernel<true><<<grid, F_THREADS, F_SMEM_TOTAL, st>>>(tq, tk, tv, *a);
   } else {
-    static bool cfg = false;
-    if (!cfg) { SC_CUDA(cudaFuncSetAttribute(attn_fwd_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, F_SMEM_TOTAL)); cfg = true; }
+    static sc_device_once once;
+    if (once.first()) { SC_CUDA(cudaFuncSetAttribute(attn_fwd_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, F_SMEM_TOTAL)); once.done(); }
     attn_fwd_tc_kernel<false><<<grid, F_THREADS, F_SMEM_TOTAL, st>>>(tq, tk, tv, *a);
   }
   SC_LAUNCH_CHECK();

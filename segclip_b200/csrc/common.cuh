@@ -38,7 +38,27 @@ void sc_set_error(const char* fmt, ...);
     }                                                                                   \
   } while (0)
 
-int sc_num_sms();
+int sc_num_sms();   // SM count of the CURRENT device (cached per device)
+
+// Once-per-(call site, device) latch for cudaFuncSetAttribute: the attribute is per device and entry points are called
+// from several host threads (autograd runs backward on its own thread), so the latch is an atomic per-device bit mask.
+// Two threads racing on the first call both set the (idempotent) attribute.
+#include <atomic>
+struct sc_device_once {
+  std::atomic<unsigned long long> mask{0};
+  bool first() {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    const unsigned long long bit = 1ull << (dev & 63);
+    if (mask.load(std::memory_order_acquire) & bit) return false;
+    return true;
+  }
+  void done() {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    mask.fetch_or(1ull << (dev & 63), std::memory_order_release);
+  }
+};
 
 // ---- dtype helpers ------------------------------------------------------------------------------
 typedef __nv_bfloat16 bf16;

@@ -314,10 +314,10 @@ template <int BN, bool A_MN, bool B_MN, int EF>
 int launch(const sc_gemm_desc* d, const CUtensorMap& ta, const CUtensorMap& tb, int splits, cudaStream_t st) {
   using Cfg = TileCfg<BN>;
   auto kern = gemm_tc_kernel<BN, A_MN, B_MN, EF>;
-  static bool configured = false;  // per template instantiation
-  if (!configured) {
+  static sc_device_once once;  // per template instantiation
+  if (once.first()) {
     SC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
-    configured = true;
+    once.done();
   }
   const int tiles_m = ceil_div(d->M, BM), tiles_n = ceil_div(d->N, BN);
   const int kb_total = ceil_div(d->K, BK);

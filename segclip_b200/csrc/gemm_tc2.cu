@@ -252,10 +252,10 @@ int launch2(const sc_gemm_desc* d, const CUtensorMap& ta, const CUtensorMap& tb,
     }
   }
   auto kern = gemm_tc2_kernel<A_MN, B_MN, EF>;
-  static bool configured = false;
-  if (!configured) {
+  static sc_device_once once;  // per template instantiation
+  if (once.first()) {
     SC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM2_BYTES));
-    configured = true;
+    once.done();
   }
   const int tiles_m = ceil_div(d->M, 256), tiles_n = ceil_div(d->N, 256);
   const int kb_total = ceil_div(d->K, BK);

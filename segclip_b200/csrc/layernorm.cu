@@ -190,8 +190,8 @@ int launch_bwd(const sc_ln_bwd_desc& d, cudaStream_t st) {
   const size_t smem = d.dx_colsum ? (size_t)8 * 3 * d.D * sizeof(float) : (d.dgamma ? (size_t)8 * 2 * d.D * sizeof(float) : 0);
 #define SC_LN_CASE(NV_)                                                                                      \
   {                                                                                                          \
-    static bool cfg = false;                                                                                 \
-    if (!cfg) { cudaFuncSetAttribute(ln_bwd_kernel<TDY, TX, TDX, NV_>, cudaFuncAttributeMaxDynamicSharedMemorySize, 98304); cfg = true; } \
+    static sc_device_once once;                                                                              \
+    if (once.first()) { cudaFuncSetAttribute(ln_bwd_kernel<TDY, TX, TDX, NV_>, cudaFuncAttributeMaxDynamicSharedMemorySize, 98304); once.done(); } \
     ln_bwd_kernel<TDY, TX, TDX, NV_><<<grid, 256, smem, st>>>(d);                                           \
   }
   switch (nv) {

@@ -11,6 +11,7 @@
 //   signal ready[p][self] = e         for all p  (st.release.sys after __threadfence_system)
 //   wait   ready[self][p] >= e        for all p  (ld.acquire.sys)
 // and, after the last reader of the gathered data, sc_p2p_release marks consumed[p][self] = e on all peers.
+#include <stdlib.h>
 #include <string.h>
 
 #include "common.cuh"
@@ -20,6 +21,15 @@ extern void sc_count_launch(int n);
 namespace {
 
 constexpr int MAX_WORLD = 16;
+
+unsigned long long p2p_timeout_ns() {
+  static const unsigned long long v = [] {
+    const char* e = getenv("SEGCLIP_P2P_TIMEOUT_S");
+    const double s = e ? atof(e) : 1800.0;
+    return (unsigned long long)((s > 0 ? s : 1800.0) * 1e9);
+  }();
+  return v;
+}
 
 struct PeerTable {
   void* buf[MAX_WORLD];        // peer data buffers (index = rank), same layout everywhere
@@ -34,11 +44,24 @@ SC_DEVINL uint32_t ld_acquire_sys(const uint32_t* p) {
   asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
 }
-SC_DEVINL void spin_until(const uint32_t* p, uint32_t epoch) {
-  unsigned long long spins = 0;
+SC_DEVINL unsigned long long globaltimer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+// Waits for a peer's flag with exponential __nanosleep back-off.  Ranks legitimately drift apart by minutes (rank-0-only
+// checkpoint + evaluation between epochs, main_task_align.py:484-490; data-loader start-up), so the dead-peer check is a
+// WALL-CLOCK limit (SEGCLIP_P2P_TIMEOUT_S, default 1800 s -- the same order as the NCCL watchdog), not a poll count.
+SC_DEVINL void spin_until(const uint32_t* p, uint32_t epoch, unsigned long long timeout_ns) {
+  if ((int)(ld_acquire_sys(p) - epoch) >= 0) return;
+  const unsigned long long t0 = globaltimer_ns();
+  unsigned ns = 32;
   while ((int)(ld_acquire_sys(p) - epoch) < 0) {
-    if (++spins > (1ull << 24)) {   // ~10 s: a peer died or the protocol is broken
-      printf("segclip_b200 p2p: peer flag timeout (want epoch %u, have %u)\n", epoch, ld_acquire_sys(p));
+    __nanosleep(ns);
+    if (ns < 4096) ns <<= 1;
+    if (globaltimer_ns() - t0 > timeout_ns) {   // a peer died or the protocol is broken: fail loudly
+      printf("segclip_b200 p2p: peer flag timeout after %llu s (want epoch %u, have %u)\n", timeout_ns / 1000000000ull, epoch,
+             ld_acquire_sys(p));
       __trap();
     }
   }
@@ -53,12 +76,13 @@ struct Segments {
 
 // Writes each segment of this rank into the same offset of every peer buffer (own buffer included).
 __global__ void __launch_bounds__(256) p2p_allgather_kernel(PeerTable tab, Segments seg, int rank, int world, uint32_t epoch,
-                                                             unsigned int* __restrict__ block_counter) {
+                                                             unsigned int* __restrict__ block_counter,
+                                                             unsigned long long timeout_ns) {
   __shared__ bool last;
   uint32_t* mypad = tab.pad[rank];
   // block 0 waits until every peer has released what this rank wrote last time, then opens the gate for the others
   if (blockIdx.x == 0) {
-    if (threadIdx.x < world) spin_until(mypad + world + threadIdx.x, epoch - 1);
+    if (threadIdx.x < world) spin_until(mypad + world + threadIdx.x, epoch - 1, timeout_ns);
     __syncthreads();
     if (threadIdx.x == 0) atomicExch(block_counter + 1, epoch);
   } else if (threadIdx.x == 0) {
@@ -89,7 +113,7 @@ __global__ void __launch_bounds__(256) p2p_allgather_kernel(PeerTable tab, Segme
   __threadfence_system();
   if (threadIdx.x < world) {
     st_release_sys(tab.pad[threadIdx.x] + rank, epoch);      // ready[p][rank] = epoch
-    spin_until(mypad + threadIdx.x, epoch);                  // ready[self][p] >= epoch
+    spin_until(mypad + threadIdx.x, epoch, timeout_ns);               // ready[self][p] >= epoch
   }
 }
 
@@ -161,7 +185,8 @@ int sc_p2p_allgather(int nseg, const void* const* srcs, const int64_t* nbytes, c
   if (blocks > 64) blocks = 64;
   if (blocks < 1) blocks = 1;
   sc_count_launch(1);
-  p2p_allgather_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(tab, seg, rank, world, epoch, (unsigned int*)scratch);
+  p2p_allgather_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(tab, seg, rank, world, epoch, (unsigned int*)scratch,
+                                                                       p2p_timeout_ns());
   SC_LAUNCH_CHECK();
   return SC_OK;
 }

@@ -58,6 +58,7 @@ class Plan:
         self.eval_tail = {"text": [], "vision": []}     # inference-only ops (hidden states of all tokens), see infer()
         self.bwd_groups = []
         self.bwd = []
+        self.slot = None        # exchange buffers of this batch size (world > 1)
 
     def f(self, op):
         self.fwd.append(op)
@@ -96,6 +97,7 @@ class Engine:
         self.use_mae, self.use_kl = bool(c["use_mae"]), bool(c["use_kl"])
         self.text_layers = c["text_layers"]
         self.plans = {}
+        self.eval_plans = {}
         self._ptr_sig = None
         self._setup_params()
         self.gather = None        # multi-GPU embedding exchange (segclip_b200.p2p), set by the module
@@ -185,6 +187,7 @@ class Engine:
         if start < self.gflat.numel():
             self.buckets.append((start, self.gflat.numel(), order[-1]))
         self.plans = {}
+        self.eval_plans = {}
 
     def _sig(self):
         self._ptr_sig = tuple(p.data_ptr() for p in self.params.values())
@@ -224,6 +227,16 @@ class Engine:
         if B not in self.plans:
             self.plans[B] = self._build(B)
         return self.plans[B]
+
+    def eval_plan(self, B):
+        """Plan for inference at batch B.  A training plan of the same batch is reused when it exists; otherwise an
+        exchange-free plan is built (local t_all / v_all, no gradient buckets): evaluation may run on one rank only
+        (main_task_align.py:484-490), so it must neither enter a collective nor re-point the exchange's buffers."""
+        if B in self.plans:
+            return self.plans[B]
+        if B not in self.eval_plans:
+            self.eval_plans[B] = self._build(B, probe=True)
+        return self.eval_plans[B]
 
     def _build(self, B, probe=False):
         pl = Plan()
@@ -562,7 +575,8 @@ class Engine:
         if self.world > 1 and not probe:
             if self.gather is None:
                 raise L.SegclipB200Error("world_size > 1: attach an exchange (segclip_b200.p2p.EmbeddingExchange) first")
-            t_all, v_all, lse_ext = self.gather.buffers(B, self.E)
+            pl.slot = self.gather.slot(B, self.E)          # per-batch-size buffers owned by the exchange
+            t_all, v_all, lse_ext = pl.slot.t_all, pl.slot.v_all, pl.slot.lse_all
             pl.bufs["c.t_all"], pl.bufs["c.v_all"] = t_all, v_all
         else:
             t_all, v_all = buf("c.t_all", (N, self.E)), buf("c.v_all", (N, self.E))
@@ -790,7 +804,7 @@ class Engine:
         no losses.  Runs the text and/or visual tower and the hidden-state tails; results are read from plan buffers."""
         if self.params_moved():
             raise L.SegclipB200Error("parameter storage moved after the engine was built; rebuild the engine")
-        pl = self.plan(B)
+        pl = self.eval_plan(B)
         b = pl.bufs
         st = L.stream()
         if ids is not None:
@@ -886,10 +900,10 @@ class Engine:
         if self.gather is None:
             raise L.SegclipB200Error("world_size > 1 but no embedding exchange is attached to the engine")
         if what == "gather_embeddings":
-            self.gather.gather_embeddings()
+            self.gather.gather_embeddings(pl.slot)
         elif what == "gather_lse":
-            self.gather.gather_lse()
+            self.gather.gather_lse(pl.slot)
         elif what == "release_exchange":
-            self.gather.release()
+            self.gather.release(pl.slot)
         else:
             raise L.SegclipB200Error("unknown collective step %r" % what)

@@ -47,6 +47,7 @@ class FusedAdaptAdamW(Optimizer):
         self.clip_grad = clip_grad
         self.clamp_max = {id(p): float(v) for p, v in (clamp_max or {}).items()}
         self._table = None
+        self._upload_done = None
         self._sig = None
         self._host = None
 
@@ -120,8 +121,11 @@ class FusedAdaptAdamW(Optimizer):
             self._table = torch.empty(len(raw), dtype=torch.uint8, device=dev)
             self._pinned = torch.empty(len(raw), dtype=torch.uint8).pin_memory()
             self._sqnorm = torch.zeros(1, dtype=torch.float32, device=dev)
+        if self._upload_done is not None:
+            self._upload_done.synchronize()      # the previous step's async H2D copy must have read the pinned table
         self._pinned.copy_(torch.frombuffer(bytearray(raw), dtype=torch.uint8))
         self._table.copy_(self._pinned, non_blocking=True)
+        self._upload_done = torch.cuda.current_stream(dev).record_event()
         lib, st_ = L.lib(), L.stream()
         max_norm = float(self.clip_grad) if self.clip_grad else 0.0
         self._sqnorm.zero_()

@@ -5,7 +5,8 @@ the reduction-free backward).
 ``CollectiveExchange`` torch.distributed.all_gather (NCCL on GPUs, gloo on CPU): the baseline comparator the
                        reference uses (diffdist all_gather, modules/util_module.py:180-190), kept for A/B runs and
                        for host-logic tests without GPUs.
-Both expose: buffers(B, E) -> (t_all [N,E], v_all [N,E], lse_all [2,N]); gather_embeddings(); gather_lse(); release().
+Both expose: slot(B, E) -> per-batch-size buffers (t_all [N,E], v_all [N,E], lse_all [2,N]); gather_embeddings(slot);
+gather_lse(slot); release(slot).  buffers(B, E) selects a slot for the slot-less forms of those calls.
 """
 import ctypes as C
 import os
@@ -84,70 +85,99 @@ class P2PChannel:
         self._opened, self._own = [], (None, None)
 
 
+class _Slot:
+    """Buffers of one (per-rank batch, embedding width) pair.  An exchange keeps one slot per batch size it has seen, so a
+    tail batch or an evaluation pass with another batch size never re-points the buffers a training plan was built on."""
+
+    def __init__(self, B, E, world):
+        self.B, self.E, self.N = B, E, B * world
+        self.t_all = self.v_all = self.lse_all = None
+        self.emb = self.lse = None          # P2PChannel pair (P2PExchange only)
+
+
 class _ExchangeBase:
     def __init__(self, group, device):
         self.group, self.device = group, device
         self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
-        self.B = self.E = None
+        self.slots = {}
+        self.cur = None
 
-    def _layout(self, B, E):
-        self.B, self.E, self.N = B, E, B * self.world
+    def slot(self, B, E):
+        """Slot for per-rank batch B (created on first use; creation is COLLECTIVE for the P2P exchange: every rank must
+        ask for a new batch size at the same point, which training loops do -- all ranks see the same batch sizes)."""
+        key = (int(B), int(E))
+        if key not in self.slots:
+            self.slots[key] = self._make(_Slot(key[0], key[1], self.world))
+        return self.slots[key]
+
+    def buffers(self, B, E):
+        """Selects (creating if needed) the slot for batch B and returns its (t_all [N,E], v_all [N,E], lse_all [2,N])."""
+        self.cur = self.slot(B, E)
+        return self.cur.t_all, self.cur.v_all, self.cur.lse_all
+
+    # slot-less calls act on the slot selected by the last buffers() call
+    def gather_embeddings(self, slot=None):
+        self._gather_embeddings(slot or self.cur)
+
+    def gather_lse(self, slot=None):
+        self._gather_lse(slot or self.cur)
+
+    def release(self, slot=None):
+        self._release(slot or self.cur)
 
 
 class P2PExchange(_ExchangeBase):
     """The product path: one NVLink P2P write kernel per exchange, no collective library call."""
 
-    def buffers(self, B, E):
-        self._layout(B, E)
-        N = self.N
-        self.emb = P2PChannel(self.group, self.device, 2 * N * E * 4)
-        self.lse = P2PChannel(self.group, self.device, 2 * N * 4)
-        self.t_all = self.emb.view(0, (N, E))
-        self.v_all = self.emb.view(N * E * 4, (N, E))
-        self.lse_all = self.lse.view(0, (2, N))
-        return self.t_all, self.v_all, self.lse_all
+    def _make(self, s):
+        N, E = s.N, s.E
+        s.emb = P2PChannel(self.group, self.device, 2 * N * E * 4)
+        s.lse = P2PChannel(self.group, self.device, 2 * N * 4)
+        s.t_all = s.emb.view(0, (N, E))
+        s.v_all = s.emb.view(N * E * 4, (N, E))
+        s.lse_all = s.lse.view(0, (2, N))
+        return s
 
-    def gather_embeddings(self):
-        B, E, N, r = self.B, self.E, self.N, self.rank
+    def _gather_embeddings(self, s):
+        B, E, N, r = s.B, s.E, s.N, self.rank
         lo = r * B
-        self.emb.allgather([(self.t_all[lo:lo + B], lo * E * 4), (self.v_all[lo:lo + B], (N + lo) * E * 4)])
+        s.emb.allgather([(s.t_all[lo:lo + B], lo * E * 4), (s.v_all[lo:lo + B], (N + lo) * E * 4)])
 
-    def gather_lse(self):
-        B, N, r = self.B, self.N, self.rank
+    def _gather_lse(self, s):
+        B, N, r = s.B, s.N, self.rank
         lo = r * B
-        self.lse.allgather([(self.lse_all[0, lo:lo + B], lo * 4), (self.lse_all[1, lo:lo + B], (N + lo) * 4)])
+        s.lse.allgather([(s.lse_all[0, lo:lo + B], lo * 4), (s.lse_all[1, lo:lo + B], (N + lo) * 4)])
 
-    def release(self):
-        self.emb.release()
-        self.lse.release()
+    def _release(self, s):
+        s.emb.release()
+        s.lse.release()
 
 
 class CollectiveExchange(_ExchangeBase):
     """Baseline comparator: library all-gather (NCCL / gloo), as the reference does through diffdist."""
 
-    def buffers(self, B, E):
-        self._layout(B, E)
+    def _make(self, s):
         dev = self.device
-        self.t_all = torch.zeros(self.N, E, device=dev)
-        self.v_all = torch.zeros(self.N, E, device=dev)
-        self.lse_all = torch.zeros(2, self.N, device=dev)
-        return self.t_all, self.v_all, self.lse_all
+        s.t_all = torch.zeros(s.N, s.E, device=dev)
+        s.v_all = torch.zeros(s.N, s.E, device=dev)
+        s.lse_all = torch.zeros(2, s.N, device=dev)
+        return s
 
-    def _gather_rows(self, full):
-        lo = self.rank * self.B
-        mine = full[lo:lo + self.B].clone()
+    def _gather_rows(self, full, B):
+        lo = self.rank * B
+        mine = full[lo:lo + B].clone()
         dist.all_gather_into_tensor(full, mine, group=self.group) if full.is_cuda else \
-            dist.all_gather(list(full.view(self.world, self.B, *full.shape[1:]).unbind(0)), mine, group=self.group)
+            dist.all_gather(list(full.view(self.world, B, *full.shape[1:]).unbind(0)), mine, group=self.group)
 
-    def gather_embeddings(self):
-        self._gather_rows(self.t_all)
-        self._gather_rows(self.v_all)
+    def _gather_embeddings(self, s):
+        self._gather_rows(s.t_all, s.B)
+        self._gather_rows(s.v_all, s.B)
 
-    def gather_lse(self):
-        self._gather_rows(self.lse_all[0])
-        self._gather_rows(self.lse_all[1])
+    def _gather_lse(self, s):
+        self._gather_rows(s.lse_all[0], s.B)
+        self._gather_rows(s.lse_all[1], s.B)
 
-    def release(self):
+    def _release(self, s):
         pass
 
 

@@ -10,3 +10,15 @@ if ROOT not in sys.path:
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
+
+
+def pytest_collection_modifyitems(config, items):
+    """`gpu`-marked tests are skipped on a machine without a CUDA device (so a plain `pytest tests` works anywhere).  On a
+    GPU box nothing is skipped: a missing libsegclip_b200.so must fail loudly there, never pass silently."""
+    import torch
+    if torch.cuda.is_available():
+        return
+    skip = pytest.mark.skip(reason="no CUDA device")
+    for item in items:
+        if "gpu" in item.keywords:
+            item.add_marker(skip)
