@@ -42,6 +42,16 @@ const char* sc_last_error(void);
 int sc_abi_version(void);
 /* number of kernels launched by this library in this process so far (bench.py: gpu_launches) */
 long long sc_launch_count(void);
+/* per-kernel-family launch counters (tests assert that the benchmark's tensor-core kernels, not a fallback, ran) */
+#define SC_K_GEMM_TC2 0     /* gemm_tc2_kernel: tcgen05 cta_group::2, 256 x 256 pair tiles */
+#define SC_K_GEMM_TC1 1     /* gemm_tc_kernel: tcgen05 cta_group::1 */
+#define SC_K_GEMM_SIMT 2    /* exact fp32 FMA kernel */
+#define SC_K_ATTN_FWD_TC 3  /* tcgen05 attention forward */
+#define SC_K_ATTN_BWD_TC 4  /* tcgen05 attention backward */
+#define SC_K_ATTN_MMA 5     /* mma.sync attention (legacy tensor path) */
+#define SC_K_ATTN_GENERIC 6 /* exact fp32 attention */
+#define SC_K_COUNT 8
+long long sc_kernel_launches(int kind);
 
 /* ------------------------------------------------------------------------------------------------
  * GEMM with fused epilogue.  Replaces every nn.Linear / `@ proj` / F.conv2d(stride=kernel) /

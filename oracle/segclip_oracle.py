@@ -345,9 +345,10 @@ def patch_embed(image, p, cfg):
     return ln(x, p, v + "ln_pre")
 
 
-def encode_image(image, p, cfg, u1, kv_layout, forced_idx=None, training=True):
+def encode_image(image, p, cfg, u1, kv_layout, forced_idx=None, training=True, forced_pool=None):
     """Main visual pass: encode_image (modules/module_clip.py:81-103) + SegViT main branch
-    (modules/module_seg_vit.py:434-448).  Returns (emb [B,E], aux)."""
+    (modules/module_seg_vit.py:434-448).  Returns (emb [B,E], aux).  ``forced_pool`` [B,D] teacher-forces the
+    per-channel arg-max of the centre max-pooling (reduced-precision comparisons only)."""
     v, t = "clip.visual.", "clip.visual.transformer."
     heads = cfg["vision_width"] // 64
     x = patch_embed(image, p, cfg)[:, 1:]                      # CLS dropped (:419)
@@ -358,6 +359,9 @@ def encode_image(image, p, cfg, u1, kv_layout, forced_idx=None, training=True):
     for i in range(12 - cfg["first_stage_layer"]):
         c = self_attn_block(c, p, f"{t}layers2.{i}.", heads)
     cls, pool_arg = c.max(dim=1, keepdim=True)
+    if forced_pool is not None:
+        pool_arg = forced_pool.unsqueeze(1)
+        cls = c.gather(1, pool_arg)
     hid = ln(torch.cat([cls, c], dim=1), p, v + "ln_post") @ p[v + "proj"]
     return hid[:, 0], dict(hard_attn=hard, soft_attn=soft, assign=idx, patches=x, centers=c, hidden=hid,
                            pool_arg=pool_arg[:, 0])
@@ -467,12 +471,12 @@ def l2_normalize(x):
 def rank_forward(p, batch, noise, cfg, kv_layout="torch18_flat", forced=None):
     """Everything of SegCLIP.forward that is rank-local: returns normalised (t, v) embeddings and
     the auxiliary (KL + MAE) loss of this rank.  ``forced`` = {"main": idx [B,L], "mae": idx
-    [B,keep-1]} teacher-forces the hard assignment."""
+    [B,keep-1]} teacher-forces the hard assignment; "pool" [B,D] the max-pooling arg-max."""
     forced = forced or {}
     ids = batch["input_ids"].view(-1, batch["input_ids"].shape[-1])
     image = batch["image"].float()[:, 0]
     t = encode_text(ids, p, cfg)
-    v, aux = encode_image(image, p, cfg, noise["u1"], kv_layout, forced.get("main"))
+    v, aux = encode_image(image, p, cfg, noise["u1"], kv_layout, forced.get("main"), forced_pool=forced.get("pool"))
     extra = torch.zeros(())
     info = dict(assign_main=aux["assign"], hard_attn=aux["hard_attn"], soft_attn=aux["soft_attn"],
                 t_raw=t, v_raw=v, pool_arg=aux["pool_arg"])

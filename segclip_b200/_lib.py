@@ -11,7 +11,8 @@ import re
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libsegclip_b200.so")
+# SEGCLIP_B200_LIB selects a variant build of the same library (A/B measurements, trace builds); never a different backend
+LIB_PATH = os.environ.get("SEGCLIP_B200_LIB") or os.path.join(_HERE, "lib", "libsegclip_b200.so")
 HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "segclip_b200.h")
 
 F32, BF16 = 0, 1
@@ -135,3 +136,12 @@ def stream():
 
 def launch_count():
     return int(lib().sc_launch_count())
+
+
+KERNEL_KINDS = {"gemm_tc2": 0, "gemm_tc1": 1, "gemm_simt": 2, "attn_fwd_tc": 3, "attn_bwd_tc": 4, "attn_mma": 5, "attn_generic": 6}
+
+
+def kernel_launches():
+    """{kernel family: launches so far in this process} (SC_K_* counters of the library)."""
+    l = lib()
+    return {k: int(l.sc_kernel_launches(v)) for k, v in KERNEL_KINDS.items()}

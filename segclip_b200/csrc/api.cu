@@ -15,7 +15,13 @@ void sc_set_error(const char* fmt, ...) {
   va_end(ap);
 }
 
+static std::atomic<long long> g_kind[SC_K_COUNT];
+
 void sc_count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+void sc_count_kernel(int kind, int n) {
+  g_launches.fetch_add(n, std::memory_order_relaxed);
+  if (kind >= 0 && kind < SC_K_COUNT) g_kind[kind].fetch_add(1, std::memory_order_relaxed);
+}
 
 int sc_num_sms() {
   static std::atomic<int> cache[64];
@@ -58,6 +64,9 @@ extern "C" {
 const char* sc_last_error(void) { return g_err; }
 int sc_abi_version(void) { return SC_ABI_VERSION; }
 long long sc_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+long long sc_kernel_launches(int kind) {
+  return (kind >= 0 && kind < SC_K_COUNT) ? g_kind[kind].load(std::memory_order_relaxed) : -1;
+}
 
 int sc_gemm(const sc_gemm_desc* d, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;

@@ -243,6 +243,7 @@ int set_smem(K kern, size_t bytes, const char* who) {
 }  // namespace
 
 extern void sc_count_launch(int n);
+extern void sc_count_kernel(int kind, int n);
 bool sc_attn_mma_supported(const sc_attn_desc* a);
 int sc_attention_fwd_mma(const sc_attn_desc* a, cudaStream_t st);
 int sc_attention_bwd_mma(const sc_attn_bwd_desc* g, float* delta, cudaStream_t st);
@@ -262,7 +263,7 @@ extern "C" int sc_attention_fwd(const sc_attn_desc* a, void* stream) {
   if (!a->force_generic && a->lse && sc_attn_mma_supported(a)) return sc_attention_fwd_mma(a, st);
   const size_t smem = sizeof(float) * ((size_t)2 * a->Lk * (a->hd + 1) + (size_t)ATT_WARPS * a->Lk + ATT_WARPS * 64);
   dim3 grid(a->H, a->B);
-  sc_count_launch(1);
+  sc_count_kernel(SC_K_ATTN_GENERIC, 1);
   if (a->dtype == SC_F32) {
     if ((rc = set_smem(attn_fwd_kernel<float>, smem, "sc_attention_fwd"))) return rc;
     attn_fwd_kernel<float><<<grid, ATT_THREADS, smem, st>>>(*a);
@@ -289,7 +290,7 @@ extern "C" int sc_attention_bwd(const sc_attn_bwd_desc* g, void* stream) {
   const size_t smem_kv = sizeof(float) * ((size_t)2 * a->Lq * (a->hd + 1) + 2 * (size_t)a->Lq +
                                           2 * (size_t)ATT_WARPS * a->Lq + 2 * ATT_WARPS * 64);
   dim3 grid(a->H, a->B);
-  sc_count_launch(2);
+  sc_count_kernel(SC_K_ATTN_GENERIC, 2);
   if (a->dtype == SC_F32) {
     if ((rc = set_smem(attn_bwd_dq_kernel<float>, smem_q, "sc_attention_bwd"))) return rc;
     if ((rc = set_smem(attn_bwd_dkv_kernel<float>, smem_kv, "sc_attention_bwd"))) return rc;

@@ -388,7 +388,7 @@ bool aligned_for_mma(const sc_attn_desc* a) {
 
 }  // namespace
 
-extern void sc_count_launch(int n);
+extern void sc_count_kernel(int kind, int n);
 
 // Whether the tensor-core kernels cover this problem (otherwise the generic fp32 kernels run).
 bool sc_attn_mma_supported(const sc_attn_desc* a) {
@@ -413,7 +413,7 @@ int sc_attention_fwd_mma(const sc_attn_desc* a, cudaStream_t st) {
   const size_t smem = (size_t)2 * lk_pad * 128;
   dim3 grid(1, a->H, a->B);
   const int AT_ = att_threads(a->Lq);
-  sc_count_launch(1);
+  sc_count_kernel(SC_K_ATTN_MMA, 1);
 #define CALL(HD_, C_)                                                                  \
   {                                                                                    \
     int rc = set_smem_attr(attn_fwd_mma_kernel<HD_, C_>, smem);                        \
@@ -434,7 +434,7 @@ int sc_attention_bwd_mma(const sc_attn_bwd_desc* g, float* delta, cudaStream_t s
   const size_t smem_kv = (size_t)2 * lq_pad * 128 + 2 * lq_pad * sizeof(float);
   dim3 grid_q(1, a->H, a->B), grid_kv(1, a->H, a->B);
   const int tq = att_threads(a->Lq), tkv = att_threads(a->Lk);
-  sc_count_launch(2);
+  sc_count_kernel(SC_K_ATTN_MMA, 2);
 #define CALL(HD_, C_)                                                                          \
   {                                                                                            \
     int rc = set_smem_attr(attn_bwd_dq_mma_kernel<HD_, C_>, smem_q);                           \

@@ -592,8 +592,10 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       for (int w = blockIdx.x; w < total; w += gridDim.x, par ^= 1) {
         const int qt = w % ntile;
         const int wn = w + gridDim.x;
+        TRACE(0, 20);
         mbar_wait(bar_load, par);
         tcgen05_fence_after();
+        TRACE(0, 21);
 #pragma unroll
         for (int kk = 0; kk < 4; ++kk) {
           const uint64_t dq_ = desc_sw128(sbase + F_SM_Q + kk * 32, 16, 1024);
@@ -601,21 +603,27 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
           tcgen05_mma_f16_e(tmem, dq_, dk_, id_s, kk > 0);
         }
         tcgen05_commit_e(bar_s);
+        TRACE(0, 22);
         mbar_wait(bar_s, par);                       // Q / K consumed: the next item's may land
+        TRACE(0, 23);
         if (wn < total) issue_qk(wn);
         mbar_wait(bar_v, par);
         mbar_wait(bar_p, par);
         tcgen05_fence_after();
+        TRACE(0, 24);
         const int nk = CAUSAL ? min(npad, ((qt * TILE + TILE + 15) & ~15)) >> 4 : npad >> 4;   // keys past the tile's last query: P = 0
         for (int kk = 0; kk < nk; ++kk) {
           const uint64_t dv_ = desc_sw128(sbase + F_SM_V + kk * 16 * 128, 8192, 1024);
           tcgen05_mma_f16_ts_e(tmem + F_TM_O, tmem + kk * 8, dv_, ID_PV, kk > 0);
         }
         tcgen05_commit_e(bar_o);
+        TRACE(0, 25);
         mbar_wait(bar_o, par);                       // V consumed
+        TRACE(0, 26);
         if (wn < total) issue_v(wn);
         mbar_wait(bar_free, par);                    // O read out: the accumulator columns may be overwritten
         tcgen05_fence_after();
+        TRACE(0, 27);
       }
     }
   } else {
@@ -742,8 +750,10 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     const int qi = qt * TILE + r;
     const bool warp_live = qt * TILE + warp * 32 < L;
     float m = -INFINITY, sum = 0.f;
+    if (warp == 0) TRACE(1, 30);
     mbar_wait(bar_s, par);
     tcgen05_fence_after();
+    if (warp == 0) TRACE(1, 31);
     if (warp_live) {
       const int kmax = CAUSAL ? min(L, qi + 1) : L;          // this row sees keys [0, kmax)
       // Both passes keep the next 32-column TMEM load in flight while the current one is processed (two register
@@ -768,6 +778,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         if (c0 + 32 < npad) max_chunk(bufb, bufa, c0 + 32);
       }
       m = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
+      if (warp == 0) TRACE(1, 32);
       const float mc = (m == -INFINITY) ? 0.f : m * c;        // dead rows (qi >= L) only
       // ---- pass 2: p = exp2(s c - m c), row sum, packed bf16 P over the consumed S columns
       float s4[4] = {0.f, 0.f, 0.f, 0.f};
@@ -805,8 +816,10 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     tcgen05_fence_before();
     __syncwarp();
     if (lane == 0) mbar_arrive(bar_p);
+    if (warp == 0) TRACE(1, 33);
     mbar_wait(bar_o, par);
     tcgen05_fence_after();
+    if (warp == 0) TRACE(1, 34);
     float o[64];
     if (warp_live) {
       tmem_ld32_nowait(tmem + lane_off + F_TM_O, o);
@@ -816,6 +829,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     tcgen05_fence_before();
     __syncwarp();
     if (lane == 0) mbar_arrive(bar_free);
+    if (warp == 0) TRACE(1, 35);
     if (warp_live && qi < L) {
       const float inv = 1.0f / sum;
       bf16* dst = (bf16*)a.o + (long)b * a.o_bs + (long)qi * a.o_rs + h * HD;
@@ -823,6 +837,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       for (int j = 0; j < 4; ++j) store16_bf16(dst + 16 * j, o + 16 * j, inv);
       a.lse[((long)b * a.H + h) * L + qi] = m * a.scale + logf(sum);
     }
+    if (warp == 0) TRACE(1, 36);
     }   // item loop
   }
   tcgen05_fence_before();
@@ -835,7 +850,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
 
 }  // namespace
 
-extern void sc_count_launch(int n);
+extern void sc_count_kernel(int kind, int n);
 
 bool sc_attn_tc_supported(const sc_attn_desc* a) {
   auto packed = [&](const void* p, long bs, long rs, int L) {
@@ -857,7 +872,7 @@ int sc_attention_bwd_tc(const sc_attn_bwd_desc* g, float* delta, cudaStream_t st
   if ((rc = sc_get_tensor_map(a->k, (uint64_t)a->H * HD, rows, a->k_rs, 64, TILE, &tk))) return rc;
   if ((rc = sc_get_tensor_map(a->v, (uint64_t)a->H * HD, rows, a->v_rs, 64, TILE, &tv))) return rc;
   if ((rc = sc_get_tensor_map(g->d_o, (uint64_t)a->H * HD, rows, a->o_rs, 64, TILE, &tdo))) return rc;
-  sc_count_launch(2);
+  sc_count_kernel(SC_K_ATTN_BWD_TC, 2);
   const long n = rows * a->H;
   attn_delta_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>((const bf16*)a->o, (const bf16*)g->d_o, a->o_bs, a->o_rs, a->B,
                                                                  a->H, L, delta);
@@ -884,7 +899,7 @@ int sc_attention_fwd_tc(const sc_attn_desc* a, cudaStream_t st) {
   if ((rc = sc_get_tensor_map(a->q, (uint64_t)a->H * HD, rows, a->q_rs, 64, TILE, &tq))) return rc;
   if ((rc = sc_get_tensor_map(a->k, (uint64_t)a->H * HD, rows, a->k_rs, 64, ntile * TILE, &tk))) return rc;
   if ((rc = sc_get_tensor_map(a->v, (uint64_t)a->H * HD, rows, a->v_rs, 64, ntile * TILE, &tv))) return rc;
-  sc_count_launch(1);
+  sc_count_kernel(SC_K_ATTN_FWD_TC, 1);
   const long total = (long)ntile * a->H * a->B;
   const long slots = 2L * sc_num_sms();
   dim3 grid((unsigned)(total < slots ? total : slots));

@@ -69,14 +69,14 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(const T* __restrict__ A,
 
 }  // namespace
 
-extern void sc_count_launch(int n);
+extern void sc_count_kernel(int kind, int n);
 
 int sc_gemm_simt(const sc_gemm_desc* d, cudaStream_t st) {
   sc_gemm_desc dd = *d;
   dd.split_k = 1;
   EpiParams ep = make_epi(&dd);
   dim3 grid(ceil_div(d->N, TN), ceil_div(d->M, TM));
-  sc_count_launch(1);
+  sc_count_kernel(SC_K_GEMM_SIMT, 1);
   if (d->in_dtype == SC_F32)
     gemm_simt_kernel<float><<<grid, 256, 0, st>>>((const float*)d->A, d->lda, d->trans_a, (const float*)d->B, d->ldb,
                                                    d->trans_b, d->K, ep);

@@ -335,7 +335,7 @@ int launch(const sc_gemm_desc* d, const CUtensorMap& ta, const CUtensorMap& tb, 
 
 }  // namespace
 
-extern void sc_count_launch(int n);
+extern void sc_count_kernel(int kind, int n);
 int sc_gemm_tc2(const sc_gemm_desc* d, cudaStream_t st);
 
 // Returns SC_ERR_UNSUPPORTED when the problem does not meet the TMA alignment rules (caller falls
@@ -386,7 +386,7 @@ int sc_gemm_tc(const sc_gemm_desc* d, cudaStream_t st) {
     sc_set_error("sc_gemm: colsum_out needs a bf16-output specialised epilogue and a 16-byte aligned pointer");
     return SC_ERR_UNSUPPORTED;
   }
-  sc_count_launch(1);
+  sc_count_kernel(SC_K_GEMM_TC1, 1);
 #define SC_L(BN_, A_, B_, EF_) return launch<BN_, A_, B_, EF_>(d, ta, tb, splits, st);
 #define SC_DISPATCH(BN_)                                                                     \
   if (!a_mn && !b_mn) {                                                                      \

@@ -274,7 +274,7 @@ int launch2(const sc_gemm_desc* d, const CUtensorMap& ta, const CUtensorMap& tb,
 
 }  // namespace
 
-extern void sc_count_launch(int n);
+extern void sc_count_kernel(int kind, int n);
 
 // Same contract as sc_gemm_tc; the caller has already validated alignment.  Returns SC_ERR_UNSUPPORTED when the shape is
 // a poor fit for 256 x 256 pair tiles (the 1-CTA kernel then runs).
@@ -306,7 +306,7 @@ int sc_gemm_tc2(const sc_gemm_desc* d, cudaStream_t st) {
     sc_set_error("sc_gemm: colsum_out needs a bf16-output specialised epilogue and a 16-byte aligned pointer");
     return SC_ERR_UNSUPPORTED;
   }
-  sc_count_launch(1);
+  sc_count_kernel(SC_K_GEMM_TC2, 1);
 #define SC_L2(A_, B_, EF_) return launch2<A_, B_, EF_>(d, ta, tb, splits, st);
   if (!a_mn && !b_mn) {
     if (ef == EF_BIAS) SC_L2(false, false, EF_BIAS)

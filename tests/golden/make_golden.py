@@ -66,7 +66,7 @@ def run_case(name):
 def _w2_worker(rank, world, port, q):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
-    torch.set_num_threads(2)
+    torch.set_num_threads(2 if world <= 2 else 1)
     cfg = so.toy_config(use_mae=True, use_kl=True)
     rh.init_dist(rank, world, port)
     model = rh.build_reference_model(cfg, rank=rank, world=world)
@@ -81,16 +81,17 @@ def _w2_worker(rank, world, port, q):
         losses = [torch.zeros(()) for _ in range(world)]
     dist.gather(loss, losses if rank == 0 else None, dst=0)
     if rank == 0:
-        q.put(dict(case="toy_heads_flat_w2", config=cfg, batch=3, kv_layout="torch18_flat", param_seed=5,
+        q.put(dict(case="toy_heads_flat_w%d" % world, config=cfg, batch=3, kv_layout="torch18_flat", param_seed=5,
                    batch_seed=6, world=world, loss=[float(x) for x in losses], grads=summarize(grads),
                    torch=torch.__version__))
     dist.barrier()
 
 
-def run_w2():
+def run_w2(world=2):
+    """W gloo processes of the unmodified reference (diffdist all-gather + DDP-style gradient mean)."""
     ctx = mp.get_context("spawn")
     q = ctx.SimpleQueue()
-    procs = [ctx.Process(target=_w2_worker, args=(r, 2, 29541, q)) for r in range(2)]
+    procs = [ctx.Process(target=_w2_worker, args=(r, world, 29541 + world, q)) for r in range(world)]
     for p in procs:
         p.start()
     out = q.get()
@@ -103,7 +104,8 @@ if __name__ == "__main__":
     assert rh.reference_available(), "needs /root/reference"
     torch.manual_seed(0)
     results = [run_case(n) for n in CASES]
-    results.append(run_w2())
+    results.append(run_w2(2))
+    results.append(run_w2(8))       # full fan-out of the 8-GPU box (epoch / consumed protocol of the P2P exchange)
     for r in results:
         path = os.path.join(HERE, r["case"] + ".json")
         with open(path, "w") as f:

@@ -27,11 +27,11 @@ def test_fp32_loss_and_grads_match_oracle_and_golden(case):
     assert abs(r["loss"] - r["golden_loss"]) <= 1e-3 * abs(r["golden_loss"])      # the unmodified reference's loss
     assert r["assign_flip_rate"] == 0.0
     assert r["max_grad_rel"] <= 1e-3, r["worst"][:5]
-    # and directly against the reference's gradient fixtures (norm + random-projection checksum)
+    # and directly against the UNMODIFIED reference's gradient fixtures (norm + random-projection checksum per tensor)
     g = load_case(case)
-    from tools.e2e_report import build_model  # noqa: F401  (model already run inside run_case)
-    errs = r["errs"]
-    assert set(k for k in g["grads"] if k not in FROZEN_STEM) <= set(errs) | set(FROZEN_STEM)
+    assert set(k for k in g["grads"] if k not in FROZEN_STEM) <= set(r["errs"]) | set(FROZEN_STEM)
+    bad = compare_grads(r["grads"], g["grads"], tol=1e-3, skip=FROZEN_STEM)
+    assert not bad, bad[:5]
 
 
 @pytest.mark.parametrize("case", ["toy_heads_flat", "vitb16_contrastive_b2", "vitb16_heads_b2"])
@@ -48,6 +48,62 @@ def test_bf16_teacher_forced(case):
     rels = sorted(v[0] for v in r["errs"].values())
     assert rels[len(rels) // 2] <= 0.08, rels[len(rels) // 2]
     assert rels[-1] <= 0.15, r["worst"][:5]
+
+
+PROD_CASES = {      # name: (batch, heads, kv_layout) -- ViT-B/16, M = B*196 >= 512: the benchmark's kernel dispatch
+    "b8_contrastive_flat": (8, False, "torch18_flat"),
+    "b16_heads_flat": (16, True, "torch18_flat"),
+    "b8_heads_per_sample": (8, True, "per_sample"),
+}
+
+
+@pytest.mark.parametrize("case", list(PROD_CASES))
+def test_bf16_production_dispatch_matches_oracle(case):
+    """The kernels that carry the benchmark -- the 2-CTA tcgen05 GEMM (M >= 512), the persistent tcgen05 attention
+    forward / backward -- inside an end-to-end loss + gradient comparison with the CPU oracle.  The gradient bound is
+    tied to the IRREDUCIBLE bf16 error: the same oracle re-run with every matrix-product operand rounded to bf16
+    (fp32 accumulation, fp32 everywhere else; oracle/bf16_emulation.py).  Measured on B200 (profiles/r2_parity_*.txt):
+    the CUDA path's per-tensor rel-L2 is 0.8-1.3x that yardstick."""
+    from oracle import segclip_oracle as so
+    from tools.e2e_report import run_config
+    B, heads, kv = PROD_CASES[case]
+    cfg = so.vit_b16_config(use_mae=heads, use_kl=heads)
+    r = run_config(cfg, B, 5, 6, "bf16", forced=True, kv=kv, verbose=False, name=case, ideal=True)
+    k = r["kernels"]
+    assert k["gemm_tc2"] >= 100 and k["attn_fwd_tc"] >= 22 and k["attn_bwd_tc"] >= 22, k     # the production kernels ran
+    assert k["attn_generic"] == 0, k
+    assert r["loss_rel"] <= 1e-2, r["loss_rel"]
+    assert r["assign_flip_rate"] == 0.0
+    assert r["min_grad_cos"] >= 0.98, r["worst"][:5]
+    assert r["median_grad_rel"] <= 1.5 * r["ideal_median_grad_rel"] + 5e-3, (r["median_grad_rel"], r["ideal_median_grad_rel"])
+    assert r["worst_vs_ideal"] <= 2.0, (r["worst_vs_ideal"], r["worst"][:5])
+
+
+def test_bf16_loss_at_benchmark_batch_256():
+    """bench.py's exact configuration (ViT-B/16, contrastive, per-GPU batch 256, bf16): loss of the CUDA path against
+    the fp32 CPU oracle's forward on the same seeded batch (no teacher forcing: the few flipped hard assignments are
+    part of the 1e-2 budget)."""
+    from oracle import segclip_oracle as so
+    from tools.e2e_report import build_model
+    from segclip_b200 import _lib
+    cfg = so.vit_b16_config()
+    params = so.init_params(cfg, seed=7)
+    batch, noise = so.make_batch(cfg, 256, seed=8)
+    with torch.no_grad():
+        ref_loss, _ = so.forward(params, batch, noise, cfg)
+    model = build_model(cfg, params, "bf16", "torch18_flat")
+    model.inject_noise({k: v.cuda() for k, v in noise.items()})
+    ids = batch["input_ids"]
+    k0 = _lib.kernel_launches()
+    loss = model(ids, torch.zeros_like(ids), batch["attention_mask"], batch["image"])
+    loss.backward()
+    torch.cuda.synchronize()
+    k1 = _lib.kernel_launches()
+    assert k1["gemm_tc2"] - k0["gemm_tc2"] >= 300, (k0, k1)
+    assert abs(float(loss) - float(ref_loss)) <= 1e-2 * abs(float(ref_loss)), (float(loss), float(ref_loss))
+    for n, p in model.named_parameters():
+        if p.grad is not None:
+            assert bool(torch.isfinite(p.grad).all()), n
 
 
 def test_bf16_unforced_loss_and_flip_rates():

@@ -3,7 +3,7 @@
 CPU (gloo, world_size 2): the library-collective comparator exchange fills the gathered buffers in rank order.
 GPU (needs >= 2 devices, `gpurun --gpus 2`): two ranks of the real CUDA path -- once with the NVLink P2P write
 kernel and once with the NCCL comparator -- reproduce the 2-rank fixture of the unmodified reference (diffdist
-all-gather + DDP gradient mean, tests/golden/toy_heads_flat_w2.json)."""
+all-gather + DDP gradient mean, tests/golden/toy_heads_flat_w2.json); `gpurun --gpus 8`: the 8-rank fixture."""
 import argparse
 import os
 
@@ -52,6 +52,7 @@ def test_collective_exchange_gloo_world2():
 def _gpu_worker(rank, world, port, mode, q):
     os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
     os.environ["SEGCLIP_EXCHANGE"] = "nccl" if mode == "nccl" else "p2p"
+    os.environ["SEGCLIP_P2P_TIMEOUT_S"] = "60"       # a protocol bug must end the test, not hang the box
     torch.cuda.set_device(rank)
     dev = torch.device("cuda", rank)
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
@@ -60,7 +61,7 @@ def _gpu_worker(rank, world, port, mode, q):
     from segclip_b200.engine import FROZEN_STEM
     from segclip_b200.modeling import SegCLIP
     from segclip_b200.p2p import EmbeddingExchange
-    g = load_case("toy_heads_flat_w2")
+    g = load_case("toy_heads_flat_w%d" % world)
     cfg = g["config"]
     args = argparse.Namespace(local_rank=rank, rank=rank, world_size=world, first_stage_layer=cfg["first_stage_layer"],
                               use_vision_mae_recon=True, use_seglabel=True, precision="fp32", kv_layout=g["kv_layout"])
@@ -74,16 +75,25 @@ def _gpu_worker(rank, world, port, mode, q):
     model.inject_noise({k: v.to(dev) for k, v in noise.items()})
     ids = batch["input_ids"]
     losses = []
-    for _ in range(2):                      # two steps: exercises the epoch / release protocol
+    for step in range(2):                   # two steps: exercises the epoch / release protocol
         model.zero_grad(set_to_none=True)
         loss = model(ids, torch.zeros_like(ids), batch["attention_mask"], batch["image"], image_seg=batch["image_seg"])
         loss.backward()
         losses.append(float(loss.detach()))
+        if mode == "p2p_eval" and step == 0 and rank == 0:
+            # rank-0-only evaluation between two training steps, with ANOTHER batch size (main_task_align.py:484-490):
+            # must neither enter a collective nor re-point the exchange buffers of the training plan, while the other
+            # rank is already waiting inside the next step's exchange
+            model.eval()
+            with torch.no_grad():
+                model.clip.encode_text(ids[:1, 0])
+                model.clip.encode_image(batch["image"][:1, 0])
+            model.train()
     grads = {}
     for n, p in model.named_parameters():
         if p.grad is not None:
             gr = p.grad.detach().clone()
-            if mode != "native":
+            if mode not in ("native",):
                 dist.all_reduce(gr)
                 gr = gr / world
             grads[n] = gr.cpu()
@@ -94,17 +104,19 @@ def _gpu_worker(rank, world, port, mode, q):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("mode", ["p2p", "nccl", "native"])
-def test_two_ranks_match_reference_fixture(mode):
-    if torch.cuda.device_count() < 2:
-        pytest.skip("needs 2 GPUs (gpurun --gpus 2)")
+@pytest.mark.parametrize("world,mode", [(2, "p2p"), (2, "nccl"), (2, "native"), (2, "p2p_eval"), (8, "native")])
+def test_ranks_match_reference_fixture(world, mode):
+    """W ranks of the real CUDA path against the W-rank fixture of the unmodified reference (W gloo processes:
+    diffdist all-gather + DDP gradient mean).  W = 8 checks the epoch / consumed flag protocol at the full fan-out of the box."""
+    if torch.cuda.device_count() < world:
+        pytest.skip("needs %d GPUs (gpurun --gpus %d)" % (world, world))
     ctx = mp.get_context("spawn")
     q = ctx.SimpleQueue()
-    port = {"p2p": 29571, "nccl": 29573, "native": 29575}[mode]
-    procs = [ctx.Process(target=_gpu_worker, args=(r, 2, port, mode, q)) for r in range(2)]
+    port = {"p2p": 29571, "nccl": 29573, "native": 29575, "p2p_eval": 29577}[mode] + 20 * (world == 8)
+    procs = [ctx.Process(target=_gpu_worker, args=(r, world, port, mode, q)) for r in range(world)]
     for p in procs:
         p.start()
-    res = [q.get() for _ in range(2)]
+    res = [q.get() for _ in range(world)]
     for p in procs:
         p.join(120)
     for rank, losses, want, bad in res:

@@ -22,17 +22,18 @@ def test_port_matches_reference_golden(case):
     assert not compare_grads(grads, g["grads"], tol=5e-4)
 
 
-def test_port_two_ranks_matches_reference_golden():
-    """W=2: diffdist all-gather + DDP mean of the reference (2 gloo processes when the fixture was
+@pytest.mark.parametrize("world", [2, 8])
+def test_port_multi_rank_matches_reference_golden(world):
+    """W=2 / W=8: diffdist all-gather + DDP mean of the reference (W gloo processes when the fixture was
     made) vs the single-process multi-rank formulation of the port."""
-    g = load_case("toy_heads_flat_w2")
+    g = load_case("toy_heads_flat_w%d" % world)
     cfg = g["config"]
     p = {k: v.clone().requires_grad_(v.is_floating_point() and k not in FROZEN)
          for k, v in so.init_params(cfg, seed=g["param_seed"]).items()}
-    bn = [so.make_batch(cfg, g["batch"], seed=g["batch_seed"], rank=r) for r in range(2)]
+    bn = [so.make_batch(cfg, g["batch"], seed=g["batch_seed"], rank=r) for r in range(world)]
     losses, _ = so.forward_multi_rank(p, [b for b, _ in bn], [n for _, n in bn], cfg)
     for mine, ref in zip(losses, g["loss"]):
         assert abs(float(mine.detach()) - ref) <= 1e-5 * abs(ref)
-    (sum(losses) / 2).backward()
+    (sum(losses) / world).backward()
     grads = {k: v.grad for k, v in p.items() if v.grad is not None}
     assert not compare_grads(grads, g["grads"], tol=5e-4)
