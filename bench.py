@@ -205,16 +205,20 @@ def main():
         net.zero_grad(set_to_none=True)
         loss = net(src["input_ids"], None, None, src["image"], image_seg=src["image_seg"] if args.heads else None)
         loss.backward()
-        return float(loss) if read_loss else loss
+        return float(loss.detach()) if read_loss else loss
 
-    def timed(src, read_loss, steps):
+    def fwd_only(src, read_loss):
+        return net(src["input_ids"], None, None, src["image"], image_seg=src["image_seg"] if args.heads else None)
+
+    def timed(src, read_loss, steps, fn=None):
+        fn = fn or step
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for _ in range(steps):
-            step(src, read_loss)
+            fn(src, read_loss)
         e1.record()
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / steps
@@ -227,8 +231,11 @@ def main():
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    for _ in range(args.warmup):
-        step(resident, False)
+    loss0 = None
+    for i in range(args.warmup):
+        l_ = step(resident, False)
+        if i == 0:
+            loss0 = float(l_.detach())          # step-0 loss of this rank (random-init weights, synthetic batch)
     if rank == 0:
         sampler.wait_ready()
         sampler.mark(True)
@@ -237,6 +244,14 @@ def main():
     launches = (_lib.launch_count() - l0) // args.steps
     step(pinned, True)
     ms_e2e = timed(pinned, True, args.steps)          # clocks are sampled over both timed regions
+    ms_fwd = timed(resident, False, args.steps, fwd_only)      # forward tape only (north_star: >= 70 % on the forward)
+    if world > 1:
+        lt = torch.tensor([loss0], device=dev)
+        lall = [torch.zeros_like(lt) for _ in range(world)]
+        dist.all_gather(lall, lt)
+        losses = [float(x) for x in lall]
+    else:
+        losses = [loss0]
     if rank == 0:
         sampler.mark(False)
     clocks = sampler.stop() if rank == 0 else None
@@ -263,6 +278,9 @@ def main():
                 "d2h_bytes_per_step": 4},
         "gpu_launches": int(launches),
         "clocks": clocks,
+        "loss_step0": losses, "loss_finite": all(x == x and abs(x) != float("inf") for x in losses),
+        "fwd_tensor_frac": {"ms_fwd": ms_fwd, "achieved_tflops_per_gpu": B * gf / 3.0 / ms_fwd, "peak": pk["tflops"],
+                            "frac": B * gf / 3.0 / ms_fwd / pk["tflops"], "flops_per_pair_gf": gf / 3.0},
         "step_tensor_frac": {"achieved_tflops_per_gpu": value / world * gf / 1e3, "peak": pk["tflops"],
                              "frac": value / world * gf / 1e3 / pk["tflops"], "flops_per_pair_gf": gf},
         "roofline": {"bound": "tensor", "achieved": gemm["tflops"], "peak": pk["tflops"], "unit": "TFLOP/s",

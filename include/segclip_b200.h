@@ -90,7 +90,7 @@ typedef struct {
   const int32_t* rowbias_idx; /* [M] or NULL */
   int32_t rowbias_mod;
   int32_t act;
-  const float* residual; /* fp32 [M, N] or NULL */
+  const void* residual; /* [M, N] or NULL, dtype residual_dtype (fp32, or bf16 with a bf16 C on the tensor-core path) */
   int64_t ldr;
   void* C;
   int64_t ldc;
@@ -105,6 +105,7 @@ typedef struct {
   int32_t mul_aux_act;
   float* colsum_out;     /* optional fp32 [N]: colsum_out[n] += sum_m C[m,n] (bias gradient fused into the dgrad that produces dY);
                             only with bf16 C on the tensor-core path */
+  int32_t residual_dtype; /* SC_F32 (default) or SC_BF16 */
 } sc_gemm_desc;
 
 int sc_gemm(const sc_gemm_desc* d, void* stream);

@@ -12,7 +12,8 @@ struct EpiParams {
   const int* rowbias_idx;
   int rowbias_mod;
   int act;
-  const float* residual;
+  const void* residual;
+  int residual_dtype;
   long ldr;
   void* C;
   long ldc;
@@ -39,6 +40,7 @@ static inline EpiParams make_epi(const sc_gemm_desc* d) {
   p.rowbias_mod = d->rowbias_mod > 0 ? d->rowbias_mod : 1;
   p.act = d->act;
   p.residual = d->residual;
+  p.residual_dtype = d->residual_dtype;
   p.ldr = d->ldr;
   p.C = d->C;
   p.ldc = d->ldc;
@@ -66,7 +68,7 @@ SC_DEVINL void epi_store_scalar(const EpiParams& p, int m, int n, float acc) {
   if (p.C2) st_any(p.C2, off, p.c2_dtype, v);
   v = act_fwd(v, p.act);
   if (p.mul_aux) v *= act_grad(ld_any(p.mul_aux, off, p.mul_aux_dtype), p.mul_aux_act);
-  if (p.residual) v += p.residual[(long)m * p.ldr + n];
+  if (p.residual) v += ld_any(p.residual, (long)m * p.ldr + n, p.residual_dtype);
   if (p.atomic) {
     atomicAdd((float*)p.C + off, v);
   } else if (p.accumulate) {
@@ -118,7 +120,7 @@ SC_DEVINL void epi_store4(const EpiParams& p, int m, int n, float4 v) {
     v.z *= act_grad(a.z, p.mul_aux_act); v.w *= act_grad(a.w, p.mul_aux_act);
   }
   if (p.residual) {
-    const float4 r = *(const float4*)(p.residual + (long)m * p.ldr + n);
+    const float4 r = ld4(p.residual, (long)m * p.ldr + n, p.residual_dtype);
     v.x += r.x; v.y += r.y; v.z += r.z; v.w += r.w;
   }
   if (p.atomic) {

@@ -125,8 +125,10 @@ int sc_select_epilogue(const sc_gemm_desc* d, int splits) {
       ef = bias ? EF_BIAS : 0;
     } else if (bias && c2 && d->c2_dtype == SC_BF16 && out_bf16 && d->act == SC_ACT_QUICKGELU && !resid && !aux) {
       ef = EF_BIAS | EF_QGELU | EF_C2;
-    } else if (bias && resid && !c2 && !aux && d->act == SC_ACT_NONE && !out_bf16) {
+    } else if (bias && resid && d->residual_dtype == SC_F32 && !c2 && !aux && d->act == SC_ACT_NONE && !out_bf16) {
       ef = EF_BIAS | EF_RESID | EF_OUT_F32;
+    } else if (bias && resid && d->residual_dtype == SC_BF16 && !c2 && !aux && d->act == SC_ACT_NONE && out_bf16) {
+      ef = EF_BIAS | EF_RESID_BF;          // bf16 residual stream (2-CTA kernel; the 1-CTA kernel takes the generic epilogue)
     } else if (aux && d->mul_aux_dtype == SC_BF16 && d->mul_aux_act == SC_ACT_QUICKGELU && !bias && !resid && !c2 &&
                d->act == SC_ACT_NONE && out_bf16) {
       ef = EF_MULAUX_QGELU;
@@ -345,7 +347,7 @@ int sc_gemm_tc(const sc_gemm_desc* d, cudaStream_t st) {
   auto aligned16 = [](const void* p) { return ((uintptr_t)p & 15) == 0; };
   if (!(d->lda % 8 == 0 && d->ldb % 8 == 0 && aligned16(d->A) && aligned16(d->B) && d->N % 8 == 0 &&
         d->ldc % 8 == 0 && aligned16(d->C) && (!d->C2 || aligned16(d->C2)) &&
-        (!d->bias || aligned16(d->bias)) && (!d->residual || (aligned16(d->residual) && d->ldr % 4 == 0)) &&
+        (!d->bias || aligned16(d->bias)) && (!d->residual || (aligned16(d->residual) && d->ldr % (d->residual_dtype == SC_BF16 ? 8 : 4) == 0)) &&
         (!d->rowbias || (aligned16(d->rowbias) && d->ld_rowbias % 4 == 0)) && (!d->mul_aux || aligned16(d->mul_aux)))) {
     sc_set_error("sc_gemm(bf16): operands must be 16-byte aligned with leading dimensions multiple of 8 "
                  "(M=%d N=%d K=%d lda=%lld ldb=%lld ldc=%lld)", d->M, d->N, d->K, (long long)d->lda,

@@ -28,7 +28,7 @@ constexpr int EPI2_STAGE_BYTES = 8192;   // per epilogue warp
 constexpr int A2_BYTES = 128 * BK * 2;
 constexpr int B2_BYTES = 128 * BK * 2;
 constexpr int STAGE2_BYTES = A2_BYTES + B2_BYTES;
-constexpr int SMEM2_BYTES = STAGES2 * STAGE2_BYTES + EPI2_WARPS * EPI2_STAGE_BYTES + 256;
+constexpr int SMEM2_BYTES = STAGES2 * STAGE2_BYTES + EPI2_WARPS * EPI2_STAGE_BYTES + 256 + EPI2_WARPS * 4 * 8;   // + input-tile mbarriers
 constexpr uint32_t PEER_MASK = 0xFEFFFFFFu;   // clears the CTA-rank bit of a shared::cluster address -> CTA 0 of the pair
 
 SC_DEVINL uint32_t cluster_ctarank() {
@@ -73,7 +73,8 @@ SC_DEVINL void mbar_arrive_leader(uint64_t* bar) {
 template <bool A_MN, bool B_MN, int EF>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS2, 1)
 gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmC2, int tiles_m, int tiles_n,
+                const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmC2,
+                const __grid_constant__ CUtensorMap tmX, int tiles_m, int tiles_n,
                 int splits, int kb_total, int kb_per_split, EpiParams ep) {
   extern __shared__ __align__(1024) uint8_t smem[];
   if ((smem_u32(smem) & 1023u) != 0u) __trap();
@@ -86,6 +87,9 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   uint64_t* tmem_full = bars + 2 * STAGES2;
   uint64_t* tmem_empty = tmem_full + 2;
   uint32_t* tmem_slot = (uint32_t*)(tmem_empty + 2);
+  uint64_t* aux_bar = (uint64_t*)(epi_stage + EPI2_WARPS * EPI2_STAGE_BYTES + 256);     // [epilogue warp][chunk]
+  constexpr bool kAux = EpiAuxTma<EF>::value;
+  static_assert(!kAux || EPI2_COLS == 128, "input-tile epilogue: one 2 KB box per chunk, four chunks per warp");
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -100,6 +104,9 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tmem_full[i], 1);
       mbar_init(&tmem_empty[i], 2 * EPI2_WARPS);
+    }
+    if constexpr (kAux) {
+      for (int i = 0; i < EPI2_WARPS * 4; ++i) mbar_init(&aux_bar[i], 1);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -194,7 +201,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     const int cgrp = warp >> 2;
     const uint32_t stage = smem_u32(epi_stage) + warp * EPI2_STAGE_BYTES;
     uint32_t g = 0;
-    const int l7 = lane & 7, l3 = lane >> 3;
+    uint32_t aux_phase = 0;          // bit c: parity of this warp's input-tile barrier c
     int it = 0;
     for (int item = pair; item < num_items; item += npairs, ++it) {
       const int nt = item % tiles_n;
@@ -202,19 +209,38 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       const int nbase = nt * 256 + cgrp * EPI2_COLS;
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
+      const int mrow0 = mt * 256 + rank * 128 + quarter * 32;
       float4 breg = make_float4(0.f, 0.f, 0.f, 0.f);
-      if constexpr (EpiTma<EF>::value && (EF & EF_BIAS) != 0) {
+      if constexpr ((EpiTma<EF>::value || kAux) && (EF & EF_BIAS) != 0) {
         if (nbase + 4 * lane < ep.N) breg = __ldg((const float4*)(ep.bias + nbase + 4 * lane));
+      }
+      if constexpr (kAux) {
+        // the four input tiles of this warp's chunks: issued now, they land under the tile's main loop
+        bulk_wait_read<0>();           // (elected lane) the previous tile's stores have read the boxes
+        __syncwarp();
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          if (nbase + c * 32 < ep.N && mrow0 < ep.M) {          // warp-uniform
+            mbar_expect_tx_e(&aux_bar[warp * 4 + c], 2048u);
+            tma_load_2d_e(&tmX, &aux_bar[warp * 4 + c], epi_stage + warp * EPI2_STAGE_BYTES + c * 2048, nbase + c * 32, mrow0);
+          }
+        }
       }
       mbar_wait(&tmem_full[acc], acc_phase);
       tcgen05_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * 256 + cgrp * EPI2_COLS;
-      const int mrow0 = mt * 256 + rank * 128 + quarter * 32;
 #pragma unroll 1
       for (int c = 0; c < EPI2_COLS / 32; ++c) {
         float v[32];
         const int n0 = nbase + c * 32;
-        if constexpr (EpiTma<EF>::value) {
+        if constexpr (kAux) {
+          tmem_ld32(taddr + c * 32, v);
+          if (n0 < ep.N && mrow0 < ep.M) {                        // warp-uniform
+            mbar_wait(&aux_bar[warp * 4 + c], (aux_phase >> c) & 1u);
+            aux_phase ^= 1u << c;
+            epi_finish_aux_tma<EF>(ep, v, stage + c * 2048, lane, mrow0, n0, c, breg, &tmC);
+          }
+        } else if constexpr (EpiTma<EF>::value) {
           tmem_ld32(taddr + c * 32, v);
           epi_finish_tma<EF>(ep, v, stage, lane, mrow0, n0, g++, c, breg, &tmC, &tmC2);
         } else {
@@ -230,7 +256,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     }
   }
 
-  if constexpr (EpiTma<EF>::value) {
+  if constexpr (EpiTma<EF>::value || kAux) {
     if (warp < EPI2_WARPS) bulk_wait_all();                  // staging smem must outlive the last TMA stores
   }
   tcgen05_fence_before();
@@ -244,6 +270,14 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 template <bool A_MN, bool B_MN, int EF>
 int launch2(const sc_gemm_desc* d, const CUtensorMap& ta, const CUtensorMap& tb, int splits, cudaStream_t st) {
   CUtensorMap tc_ = ta, tc2_ = ta;          // placeholders for the kinds that do not store through the TMA
+  CUtensorMap tx_ = ta;
+  if constexpr (EpiAuxTma<EF>::value) {
+    int rc;
+    if ((rc = sc_get_tensor_map_sw(d->C, d->N, d->M, d->ldc, 32, 32, 64, &tc_))) return rc;
+    if constexpr ((EF & EF_RESID_BF) != 0) rc = sc_get_tensor_map_sw(d->residual, d->N, d->M, d->ldr, 32, 32, 64, &tx_);
+    else rc = sc_get_tensor_map_sw(d->mul_aux, d->N, d->M, d->ldc, 32, 32, 64, &tx_);
+    if (rc) return rc;
+  }
   if constexpr (EpiTma<EF>::value) {
     int rc;
     if ((rc = sc_get_tensor_map_sw(d->C, d->N, d->M, d->ldc, 32, 32, 64, &tc_))) return rc;
@@ -267,7 +301,7 @@ int launch2(const sc_gemm_desc* d, const CUtensorMap& ta, const CUtensorMap& tb,
   const int items = tiles_m * tiles_n * splits;
   const int max_pairs = sc_num_sms() / 2;
   const int pairs = items < max_pairs ? items : max_pairs;
-  kern<<<2 * pairs, THREADS2, SMEM2_BYTES, st>>>(ta, tb, tc_, tc2_, tiles_m, tiles_n, splits, kb_total, kb_per, ep);
+  kern<<<2 * pairs, THREADS2, SMEM2_BYTES, st>>>(ta, tb, tc_, tc2_, tx_, tiles_m, tiles_n, splits, kb_total, kb_per, ep);
   SC_LAUNCH_CHECK();
   return SC_OK;
 }
@@ -313,6 +347,7 @@ int sc_gemm_tc2(const sc_gemm_desc* d, cudaStream_t st) {
     if (ef == 0) SC_L2(false, false, 0)
     if (ef == (EF_BIAS | EF_QGELU | EF_C2)) SC_L2(false, false, EF_BIAS | EF_QGELU | EF_C2)
     if (ef == (EF_BIAS | EF_RESID | EF_OUT_F32)) SC_L2(false, false, EF_BIAS | EF_RESID | EF_OUT_F32)
+    if (ef == (EF_BIAS | EF_RESID_BF)) SC_L2(false, false, EF_BIAS | EF_RESID_BF)
     if (ef == (EF_BIAS | EF_GELU | EF_C2)) SC_L2(false, false, EF_BIAS | EF_GELU | EF_C2)
     if (ef == EF_OUT_F32) SC_L2(false, false, EF_OUT_F32)
     SC_L2(false, false, EF_GENERIC)

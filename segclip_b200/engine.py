@@ -867,6 +867,7 @@ class Engine:
         pl = self.plan(B)
         st = L.stream()
         recs = []
+        dense = (self.kdense, self.vdense, self.dkdense, self.dvdense)
 
         def run(op):
             if isinstance(op, str):      # exchanges are skipped: this instrumented pass may run on one rank only
@@ -879,7 +880,10 @@ class Engine:
                 e0.record()
                 op(st)
                 e1.record()
-                recs.append((e0, e1, 2.0 * d.M * d.N * d.K))
+                fl = 2.0 * d.M * d.N * d.K
+                if any(t is x for t in op.keep[1:4] for x in dense):
+                    fl /= self.Hv          # grouped 1x1 conv run as a dense block-diagonal GEMM: algorithmic = 1/groups
+                recs.append((e0, e1, fl))
             else:
                 op(st)
 

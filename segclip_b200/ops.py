@@ -65,8 +65,8 @@ def gemm_desc(A, B, C_, *, trans_a=False, trans_b=False, bias=None, rowbias=None
     d.act = act
     if residual is not None:
         _chk2d(residual)
-        assert residual.dtype == torch.float32 and residual.shape == C_.shape
-        d.residual, d.ldr = residual.data_ptr(), residual.stride(0)
+        assert residual.shape == C_.shape and (residual.dtype == torch.float32 or residual.dtype == C_.dtype), (residual.dtype, C_.dtype)
+        d.residual, d.ldr, d.residual_dtype = residual.data_ptr(), residual.stride(0), L.dt(residual)
     d.C, d.ldc, d.c_dtype = C_.data_ptr(), C_.stride(0), L.dt(C_)
     if C2 is not None:
         _chk2d(C2)
@@ -119,7 +119,6 @@ def layernorm_bwd_op(dy, x, mean, rstd, gamma, dx=None, accumulate_dx=False, dx_
     d.mean, d.rstd, d.gamma = mean.data_ptr(), rstd.data_ptr(), gamma.data_ptr()
     if dx is not None:
         d.dx, d.dx_dtype = dx.data_ptr(), L.dt(dx)
-        assert not accumulate_dx or dx.dtype == torch.float32
     d.accumulate_dx = int(accumulate_dx)
     if dx_copy is not None:
         assert dx_copy.dtype == torch.bfloat16 and dx is not None
