@@ -241,7 +241,8 @@ int sc_u8_normalize(const uint8_t* img, float* out, int64_t n, int hw, const flo
  * b*T + argmax_t ids[b,t] of the EOT token (:136). */
 int sc_text_embed(const int64_t* ids, const float* tok, const float* pos, float* out, int32_t* eot_rows, int B, int T,
                   int W, void* stream);
-int sc_gather_rows(const float* src, const int32_t* idx, float* out, int64_t rows, int D, void* stream);
+/* out[r,:] = src[idx[r],:]; src in src_dtype (fp32, or the bf16 residual stream), out fp32 */
+int sc_gather_rows(const void* src, int src_dtype, const int32_t* idx, float* out, int64_t rows, int D, void* stream);
 int sc_scatter_rows(const float* src, const int32_t* idx, float* out, int64_t rows, int D, void* stream);
 
 /* random_masking(keep_cls=True) (modules/module_clip_util.py:91-124) from an explicit uniform draw u

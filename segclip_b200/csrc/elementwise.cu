@@ -186,10 +186,10 @@ __global__ void eot_index_kernel(const long long* __restrict__ ids, int* __restr
   eot_rows[b] = b * T + arg;
 }
 
-__global__ void gather_rows_kernel(const float* __restrict__ src, const int* __restrict__ idx, float* __restrict__ out, int D) {
+__global__ void gather_rows_kernel(const void* __restrict__ src, int sdt, const int* __restrict__ idx, float* __restrict__ out, int D) {
   const long r = blockIdx.x;
   const long s = idx[r];
-  for (int d = threadIdx.x; d < D; d += blockDim.x) out[r * D + d] = src[s * D + d];
+  for (int d = threadIdx.x; d < D; d += blockDim.x) out[r * D + d] = ld_any(src, s * D + d, sdt);
 }
 __global__ void scatter_rows_kernel(const float* __restrict__ src, const int* __restrict__ idx, float* __restrict__ out, int D) {
   const long r = blockIdx.x;
@@ -367,10 +367,10 @@ int sc_text_embed(const int64_t* ids, const float* tok, const float* pos, float*
   return SC_OK;
 }
 
-int sc_gather_rows(const float* src, const int32_t* idx, float* out, int64_t rows, int D, void* stream) {
+int sc_gather_rows(const void* src, int src_dtype, const int32_t* idx, float* out, int64_t rows, int D, void* stream) {
   SC_CHECK_ARG(src && idx && out && rows > 0, "sc_gather_rows: bad args");
   sc_count_launch(1);
-  gather_rows_kernel<<<(unsigned)rows, 128, 0, (cudaStream_t)stream>>>(src, idx, out, D);
+  gather_rows_kernel<<<(unsigned)rows, 128, 0, (cudaStream_t)stream>>>(src, src_dtype, idx, out, D);
   SC_LAUNCH_CHECK();
   return SC_OK;
 }

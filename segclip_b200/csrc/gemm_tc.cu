@@ -69,9 +69,15 @@ int sc_get_tensor_map(const void* ptr, uint64_t dim0, uint64_t dim1, uint64_t st
 // same with an explicit swizzle span in bytes (128 or 64; 64 is used by the TMA-store epilogue's 32 x 32 bf16 boxes)
 int sc_get_tensor_map_sw(const void* ptr, uint64_t dim0, uint64_t dim1, uint64_t stride_elems, uint32_t box0, uint32_t box1,
                          int swizzle_bytes, CUtensorMap* out) {
+  return sc_get_tensor_map_any(ptr, dim0, dim1, stride_elems, box0, box1, swizzle_bytes, 2, out);
+}
+
+// element size 2 = bf16, 4 = fp32 (fp32 residual / output boxes of the GEMM epilogue)
+int sc_get_tensor_map_any(const void* ptr, uint64_t dim0, uint64_t dim1, uint64_t stride_elems, uint32_t box0, uint32_t box1,
+                          int swizzle_bytes, int elem_bytes, CUtensorMap* out) {
   static std::mutex mu;
   static std::unordered_map<MapKey, CUtensorMap, MapKeyHash> cache;
-  MapKey key{ptr, dim0, dim1, stride_elems, box0, box1, swizzle_bytes};
+  MapKey key{ptr, dim0, dim1, stride_elems, box0, box1, swizzle_bytes | (elem_bytes << 16)};
   {
     std::lock_guard<std::mutex> g(mu);
     auto it = cache.find(key);
@@ -86,10 +92,10 @@ int sc_get_tensor_map_sw(const void* ptr, uint64_t dim0, uint64_t dim1, uint64_t
     return SC_ERR_CUDA;
   }
   cuuint64_t gdim[2] = {dim0, dim1};
-  cuuint64_t gstride[1] = {stride_elems * 2};
+  cuuint64_t gstride[1] = {stride_elems * (uint64_t)elem_bytes};
   cuuint32_t box[2] = {box0, box1};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), gdim, gstride, box, estr,
+  CUresult r = enc(out, elem_bytes == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), gdim, gstride, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);

@@ -88,8 +88,12 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   uint64_t* tmem_empty = tmem_full + 2;
   uint32_t* tmem_slot = (uint32_t*)(tmem_empty + 2);
   uint64_t* aux_bar = (uint64_t*)(epi_stage + EPI2_WARPS * EPI2_STAGE_BYTES + 256);     // [epilogue warp][chunk]
-  constexpr bool kAux = EpiAuxTma<EF>::value;
-  static_assert(!kAux || EPI2_COLS == 128, "input-tile epilogue: one 2 KB box per chunk, four chunks per warp");
+  constexpr bool kAux = EpiAuxTma<EF>::value;      // bf16 input tile (residual / activation-gradient operand): 4 boxes of 2 KB
+  constexpr bool kRes = EpiResTma<EF>::value;      // fp32 residual tile: 2 boxes of 4 KB
+  constexpr bool kIn = kAux || kRes;
+  constexpr int NBOX = kRes ? 2 : 4;
+  constexpr uint32_t BOXB = kRes ? 4096u : 2048u;
+  static_assert(!kIn || EPI2_COLS == 128, "input-tile epilogue: four chunks per warp and tile");
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -105,7 +109,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       mbar_init(&tmem_full[i], 1);
       mbar_init(&tmem_empty[i], 2 * EPI2_WARPS);
     }
-    if constexpr (kAux) {
+    if constexpr (kIn) {
       for (int i = 0; i < EPI2_WARPS * 4; ++i) mbar_init(&aux_bar[i], 1);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -211,20 +215,20 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       const uint32_t acc_phase = (it >> 1) & 1;
       const int mrow0 = mt * 256 + rank * 128 + quarter * 32;
       float4 breg = make_float4(0.f, 0.f, 0.f, 0.f);
-      if constexpr ((EpiTma<EF>::value || kAux) && (EF & EF_BIAS) != 0) {
+      if constexpr ((EpiTma<EF>::value || kIn) && (EF & EF_BIAS) != 0) {
         if (nbase + 4 * lane < ep.N) breg = __ldg((const float4*)(ep.bias + nbase + 4 * lane));
       }
-      if constexpr (kAux) {
-        // the four input tiles of this warp's chunks: issued now, they land under the tile's main loop
+      auto issue_in = [&](int c) {                                // input tile of chunk c -> box c % NBOX (whole warp calls)
+        mbar_expect_tx_e(&aux_bar[warp * 4 + c % NBOX], BOXB);
+        tma_load_2d_e(&tmX, &aux_bar[warp * 4 + c % NBOX], epi_stage + warp * EPI2_STAGE_BYTES + (c % NBOX) * BOXB, nbase + c * 32, mrow0);
+      };
+      if constexpr (kIn) {
+        // the input tiles of this warp's first chunks: issued now, they land under the tile's main loop
         bulk_wait_read<0>();           // (elected lane) the previous tile's stores have read the boxes
         __syncwarp();
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          if (nbase + c * 32 < ep.N && mrow0 < ep.M) {          // warp-uniform
-            mbar_expect_tx_e(&aux_bar[warp * 4 + c], 2048u);
-            tma_load_2d_e(&tmX, &aux_bar[warp * 4 + c], epi_stage + warp * EPI2_STAGE_BYTES + c * 2048, nbase + c * 32, mrow0);
-          }
-        }
+        for (int c = 0; c < NBOX; ++c)
+          if (nbase + c * 32 < ep.N && mrow0 < ep.M) issue_in(c);          // warp-uniform
       }
       mbar_wait(&tmem_full[acc], acc_phase);
       tcgen05_fence_after();
@@ -233,12 +237,19 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       for (int c = 0; c < EPI2_COLS / 32; ++c) {
         float v[32];
         const int n0 = nbase + c * 32;
-        if constexpr (kAux) {
+        if constexpr (kIn) {
           tmem_ld32(taddr + c * 32, v);
           if (n0 < ep.N && mrow0 < ep.M) {                        // warp-uniform
-            mbar_wait(&aux_bar[warp * 4 + c], (aux_phase >> c) & 1u);
-            aux_phase ^= 1u << c;
-            epi_finish_aux_tma<EF>(ep, v, stage + c * 2048, lane, mrow0, n0, c, breg, &tmC);
+            const int bx = c % NBOX;
+            mbar_wait(&aux_bar[warp * 4 + bx], (aux_phase >> bx) & 1u);
+            aux_phase ^= 1u << bx;
+            if constexpr (kAux) epi_finish_aux_tma<EF>(ep, v, stage + bx * BOXB, lane, mrow0, n0, c, breg, &tmC);
+            else epi_finish_res_tma<EF>(ep, v, stage + bx * BOXB, lane, mrow0, n0, c, breg, &tmC);
+            if (NBOX < 4 && c + NBOX < 4 && n0 + NBOX * 32 < ep.N) {      // box reused within the tile (fp32 boxes)
+              bulk_wait_read<0>();
+              __syncwarp();
+              issue_in(c + NBOX);
+            }
           }
         } else if constexpr (EpiTma<EF>::value) {
           tmem_ld32(taddr + c * 32, v);
@@ -256,7 +267,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     }
   }
 
-  if constexpr (EpiTma<EF>::value || kAux) {
+  if constexpr (EpiTma<EF>::value || kIn) {
     if (warp < EPI2_WARPS) bulk_wait_all();                  // staging smem must outlive the last TMA stores
   }
   tcgen05_fence_before();
@@ -277,6 +288,11 @@ int launch2(const sc_gemm_desc* d, const CUtensorMap& ta, const CUtensorMap& tb,
     if constexpr ((EF & EF_RESID_BF) != 0) rc = sc_get_tensor_map_sw(d->residual, d->N, d->M, d->ldr, 32, 32, 64, &tx_);
     else rc = sc_get_tensor_map_sw(d->mul_aux, d->N, d->M, d->ldc, 32, 32, 64, &tx_);
     if (rc) return rc;
+  }
+  if constexpr (EpiResTma<EF>::value) {
+    int rc;
+    if ((rc = sc_get_tensor_map_any(d->C, d->N, d->M, d->ldc, 32, 32, 128, 4, &tc_))) return rc;
+    if ((rc = sc_get_tensor_map_any(d->residual, d->N, d->M, d->ldr, 32, 32, 128, 4, &tx_))) return rc;
   }
   if constexpr (EpiTma<EF>::value) {
     int rc;

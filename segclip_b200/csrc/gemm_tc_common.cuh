@@ -497,6 +497,42 @@ SC_DEVINL void epi_finish_aux_tma(const EpiParams& ep, float (&v)[32], uint32_t 
   }
 }
 
+// ---- fp32 residual stream (out_proj / c_proj forward): C(fp32) = acc + bias + residual(fp32), both through the TMA ----
+// Same idea with 32 x 32 fp32 boxes (4 KB, SWIZZLE_128B): a warp's 8 KB of staging hold two, so the loads of chunks 2 and
+// 3 are issued as soon as the stores of chunks 0 and 1 have read their box.
+template <int EF>
+struct EpiResTma {
+  static constexpr bool value = (EF != EF_GENERIC) && (EF & EF_RESID) != 0 && (EF & EF_OUT_F32) != 0 &&
+                                (EF & (EF_ATOMIC | EF_ACCUM | EF_C2 | EF_MULAUX_QGELU | EF_MULAUX_GELU | EF_QGELU | EF_GELU)) == 0;
+};
+
+template <int EF>
+SC_DEVINL void epi_finish_res_tma(const EpiParams& ep, float (&v)[32], uint32_t box, int lane, int mrow0, int n0, int c,
+                                  const float4& breg, const CUtensorMap* tmC) {
+  if constexpr ((EF & EF_BIAS) != 0) {
+    const int src = c * 8;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      v[4 * j] += __shfl_sync(0xffffffffu, breg.x, src + j);
+      v[4 * j + 1] += __shfl_sync(0xffffffffu, breg.y, src + j);
+      v[4 * j + 2] += __shfl_sync(0xffffffffu, breg.z, src + j);
+      v[4 * j + 3] += __shfl_sync(0xffffffffu, breg.w, src + j);
+    }
+  }
+  const uint32_t row = box + lane * 128;
+  const int sw = lane & 7;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const uint32_t a = row + ((j ^ sw) << 4);
+    const float4 r = lds128(a);
+    sts128(a, v[4 * j] + r.x, v[4 * j + 1] + r.y, v[4 * j + 2] + r.z, v[4 * j + 3] + r.w);
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  __syncwarp();
+  tma_store_2d(tmC, box, n0, mrow0);
+  bulk_commit();
+}
+
 // one warp, one chunk of 32 rows x 32 accumulator columns; `g` = running chunk counter of the warp (buffer rotation)
 template <int EF>
 SC_DEVINL void epi_finish_tma(const EpiParams& ep, float (&v)[32], uint32_t stage, int lane, int mrow0, int n0, uint32_t g,
@@ -590,4 +626,6 @@ int sc_get_tensor_map(const void* ptr, uint64_t dim0, uint64_t dim1, uint64_t st
                       CUtensorMap* out);
 int sc_get_tensor_map_sw(const void* ptr, uint64_t dim0, uint64_t dim1, uint64_t stride_elems, uint32_t box0, uint32_t box1,
                          int swizzle_bytes, CUtensorMap* out);
+int sc_get_tensor_map_any(const void* ptr, uint64_t dim0, uint64_t dim1, uint64_t stride_elems, uint32_t box0, uint32_t box1,
+                          int swizzle_bytes, int elem_bytes, CUtensorMap* out);
 int sc_select_epilogue(const sc_gemm_desc* d, int splits);

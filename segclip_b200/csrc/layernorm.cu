@@ -2,6 +2,8 @@
 // Replaces modules/module_clip_util.py:126-132 (LayerNorm, fp32 statistics) and the nn.LayerNorm
 // instances in modules/module_seg_vit.py:256,264,267,272 and modules/module_mae.py:146,149,239.
 // HBM-bound: read x once, write y once (fwd); read dy, x once, write dx once (bwd).
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace {
@@ -163,6 +165,158 @@ __global__ void __launch_bounds__(256, 3) ln_bwd_kernel(sc_ln_bwd_desc d) {
   }
 }
 
+
+// ---- register-accumulator backward (D % 8 == 0): the production kernel ---------------------------------------------
+// One warp per row, 8-element vectors (16-byte loads of bf16 data).  dgamma / dbeta / colsum(dx) partial sums live in
+// REGISTERS (8 * NV8 each) for the whole grid-stride loop and are reduced across the CTA's warps once at the end.  The
+// first version kept them in per-warp shared-memory slices (2-3 vector load-add-store per 4 elements): with the bf16
+// gradient stream the kernel moves 10 B per element instead of 16 and that smem traffic, not HBM, became the limit
+// (3.0 TB/s).  128-thread CTAs, 3 per SM.
+template <typename T> SC_DEVINL void ld8(const T* p, float (&v)[8]);
+template <> SC_DEVINL void ld8<float>(const float* p, float (&v)[8]) {
+  const float4 a = *(const float4*)p, b = *(const float4*)(p + 4);
+  v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+}
+template <> SC_DEVINL void ld8<bf16>(const bf16* p, float (&v)[8]) {
+  const uint4 u = *(const uint4*)p;
+  const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float2 f = __bfloat1622float2(*(const __nv_bfloat162*)&w[i]);
+    v[2 * i] = f.x;
+    v[2 * i + 1] = f.y;
+  }
+}
+template <typename T> SC_DEVINL void st8(T* p, const float (&v)[8]);
+template <> SC_DEVINL void st8<float>(float* p, const float (&v)[8]) {
+  *(float4*)p = make_float4(v[0], v[1], v[2], v[3]);
+  *(float4*)(p + 4) = make_float4(v[4], v[5], v[6], v[7]);
+}
+template <> SC_DEVINL void st8<bf16>(bf16* p, const float (&v)[8]) {
+  uint4 u;
+  __nv_bfloat162 a = __floats2bfloat162_rn(v[0], v[1]), b = __floats2bfloat162_rn(v[2], v[3]);
+  __nv_bfloat162 c = __floats2bfloat162_rn(v[4], v[5]), e = __floats2bfloat162_rn(v[6], v[7]);
+  u.x = *(uint32_t*)&a; u.y = *(uint32_t*)&b; u.z = *(uint32_t*)&c; u.w = *(uint32_t*)&e;
+  *(uint4*)p = u;
+}
+
+constexpr int LNB_WARPS = 4;
+
+template <typename TDY, typename TX, typename TDX, int NV8, bool CS>
+__global__ void __launch_bounds__(LNB_WARPS * 32, NV8 >= 4 ? 2 : 3) ln_bwd8_kernel(sc_ln_bwd_desc d) {
+  __shared__ float red[LNB_WARPS][1024];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int D8 = d.D >> 3;
+  const bool want_param = d.dgamma != nullptr;
+  const bool acc = d.dx && d.accumulate_dx;
+  float dg[NV8][8], db[NV8][8], cs[CS ? NV8 : 1][8];
+#pragma unroll
+  for (int j = 0; j < NV8; ++j)
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      dg[j][k] = 0.f;
+      db[j][k] = 0.f;
+      if (CS) cs[j][k] = 0.f;
+    }
+  for (long row = (long)blockIdx.x * LNB_WARPS + warp; row < d.rows; row += (long)gridDim.x * LNB_WARPS) {
+    const TX* x = (const TX*)d.x + row * d.D;
+    const TDY* dy = (const TDY*)d.dy + remap_row(row, d.in_group, d.out_group, d.out_off) * d.D;
+    float xv[NV8][8], dv[NV8][8], old[NV8][8];
+#pragma unroll
+    for (int j = 0; j < NV8; ++j) {      // every global read of the row is issued up front
+      const int c8 = lane + 32 * j;
+      if (c8 < D8) {
+        ld8<TX>(x + c8 * 8, xv[j]);
+        ld8<TDY>(dy + c8 * 8, dv[j]);
+        if (acc) ld8<TDX>((const TDX*)d.dx + row * d.D + c8 * 8, old[j]);
+      }
+    }
+    const float mean = d.mean[row], rstd = d.rstd[row];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int j = 0; j < NV8; ++j) {
+      const int c8 = lane + 32 * j;
+      if (c8 < D8) {
+        float gm[8];
+        ld8<float>(d.gamma + c8 * 8, gm);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const float xh = (xv[j][k] - mean) * rstd;
+          const float g = dv[j][k] * gm[k];
+          s1 += g;
+          s2 = fmaf(g, xh, s2);
+          dg[j][k] = fmaf(dv[j][k], xh, dg[j][k]);
+          db[j][k] += dv[j][k];
+          xv[j][k] = xh;
+          dv[j][k] = g;
+        }
+      }
+    }
+    const float c1 = warp_sum(s1) / d.D, c2 = warp_sum(s2) / d.D;
+    if (d.dx) {
+      TDX* dx = (TDX*)d.dx + row * d.D;
+#pragma unroll
+      for (int j = 0; j < NV8; ++j) {
+        const int c8 = lane + 32 * j;
+        if (c8 < D8) {
+          float o[8];
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            o[k] = rstd * (dv[j][k] - c1 - xv[j][k] * c2);
+            if (acc) o[k] += old[j][k];
+            if (CS) cs[j][k] += o[k];
+          }
+          st8<TDX>(dx + c8 * 8, o);
+          if (d.dx_copy_bf16) st8<bf16>((bf16*)d.dx_copy_bf16 + row * d.D + c8 * 8, o);
+        }
+      }
+    }
+  }
+  if (!want_param && !CS) return;
+  // cross-warp reduction, one array at a time: registers -> smem slice per warp -> one atomic per column and CTA
+#pragma unroll
+  for (int which = 0; which < (CS ? 3 : 2); ++which) {
+    float* dst = which == 0 ? d.dgamma : (which == 1 ? d.dbeta : d.dx_colsum);
+    if (dst == nullptr) continue;          // uniform
+#pragma unroll
+    for (int j = 0; j < NV8; ++j) {
+      const int c8 = lane + 32 * j;
+      if (c8 < D8) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) red[warp][c8 * 8 + k] = which == 0 ? dg[j][k] : (which == 1 ? db[j][k] : cs[CS ? j : 0][k]);
+      }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < d.D; i += LNB_WARPS * 32) {
+      float s = 0.f;
+#pragma unroll
+      for (int w = 0; w < LNB_WARPS; ++w) s += red[w][i];
+      atomicAdd(dst + i, s);
+    }
+    __syncthreads();
+  }
+}
+
+template <typename TDY, typename TX, typename TDX>
+int launch_bwd8(const sc_ln_bwd_desc& d, cudaStream_t st) {
+  const int nv = ceil_div(d.D, 256);
+  long g = ceil_div(d.rows, LNB_WARPS);
+  const long per_sm = nv >= 4 ? 2 : 3;                                         // resident CTAs per SM (register budget)
+  const int grid = (int)(g < per_sm * sc_num_sms() ? g : per_sm * sc_num_sms());
+#define SC_LN8_CASE(NV_)                                                                     \
+  if (d.dx_colsum) ln_bwd8_kernel<TDY, TX, TDX, NV_, true><<<grid, LNB_WARPS * 32, 0, st>>>(d); \
+  else ln_bwd8_kernel<TDY, TX, TDX, NV_, false><<<grid, LNB_WARPS * 32, 0, st>>>(d);
+  switch (nv) {
+    case 1: SC_LN8_CASE(1); break;
+    case 2: SC_LN8_CASE(2); break;
+    case 3: SC_LN8_CASE(3); break;
+    default: SC_LN8_CASE(4); break;
+  }
+#undef SC_LN8_CASE
+  SC_LAUNCH_CHECK();
+  return SC_OK;
+}
+
 template <typename TX, typename TY>
 int launch_fwd(const sc_ln_desc& d, cudaStream_t st) {
   const int nv = ceil_div(d.D, 128);
@@ -235,6 +389,20 @@ extern "C" int sc_layernorm_bwd(const sc_ln_bwd_desc* d, void* stream) {
   if (d->rows <= 0) return SC_OK;
   sc_count_launch(1);
   const int key = d->dy_dtype * 4 + d->x_dtype * 2 + d->dx_dtype;
+  static const bool old_kernel = getenv("SC_LN_BWD_SMEM") != nullptr;      // A/B switch: shared-memory accumulator version
+  if (!old_kernel && d->D % 8 == 0 && d->D <= 1024 &&
+      ((uintptr_t)d->x & 15) == 0 && ((uintptr_t)d->dy & 15) == 0 && ((uintptr_t)d->dx & 15) == 0 && ((uintptr_t)d->gamma & 15) == 0) {
+    switch (key) {
+      case 0: return launch_bwd8<float, float, float>(*d, st);
+      case 1: return launch_bwd8<float, float, bf16>(*d, st);
+      case 2: return launch_bwd8<float, bf16, float>(*d, st);
+      case 3: return launch_bwd8<float, bf16, bf16>(*d, st);
+      case 4: return launch_bwd8<bf16, float, float>(*d, st);
+      case 5: return launch_bwd8<bf16, float, bf16>(*d, st);
+      case 6: return launch_bwd8<bf16, bf16, float>(*d, st);
+      case 7: return launch_bwd8<bf16, bf16, bf16>(*d, st);
+    }
+  }
   switch (key) {
     case 0: return launch_bwd<float, float, float>(*d, st);
     case 1: return launch_bwd<float, float, bf16>(*d, st);

@@ -310,7 +310,8 @@ class Engine:
 
         def ln_bwd(dy, x, stats, pre, dx=None, acc=False, dx_copy=None, remap=None, colsum=None):
             return ops.layernorm_bwd_op(dy, x, stats[0], stats[1], self.P(pre + ".weight"), dx, acc,
-                                        dx_copy if is_bf16 else None, self.grads[pre + ".weight"], self.grads[pre + ".bias"],
+                                        dx_copy if (is_bf16 and dx_copy is not dx) else None,
+                                        self.grads[pre + ".weight"], self.grads[pre + ".bias"],
                                         remap, colsum)
 
         def mlp(x_mid, x_out, dx, dxT, pre, nm, tag, eps, act, bo_grad=None):
@@ -336,8 +337,14 @@ class Engine:
 
         def block(x_in, dx, dxT, pre, nm, tag, Bn, Lseq, H, causal=False, eps=1e-5, act=ops.ACT_QUICKGELU, prev=None):
             """Pre-LN residual block (module_seg_vit.py:191-196, module_clip_ttransformer.py:48-52,
-            module_mae.py:199-201).  dx/dxT: gradient of the stream (fp32 + compute-dtype twin)."""
+            module_mae.py:199-201).  The forward residual stream is fp32 (like the reference and like autocast: rounding it
+            to bf16 after every add was emulated on the oracle -- bias / LayerNorm gradients move by 0.25-0.35 rel-L2, three
+            times the operand-rounding floor).  dx/dxT: gradient of the stream, two layouts:
+              * dx is dxT -- ONE buffer in the compute dtype (the big streams: text, layers0 main / MAE pass): LayerNorm
+                backward accumulates into it in place; the same emulation shows no measurable cost (max rel-L2 unchanged);
+              * dx fp32 + dxT compute-dtype twin (small streams fed by fp32-only glue kernels)."""
             M, D = x_in.shape
+            sdt = f32
             hd = D // H
             h1 = buf(tag + ".ln1", (M, D), T)
             st1 = ln_fwd(x_in, pre + nm["ln1"], h1, tag + ".ln1", eps)
@@ -348,13 +355,14 @@ class Engine:
             ad = ops.attn_desc(qkv, qkv[:, D:], qkv[:, 2 * D:], att, lse, Bn, H, Lseq, Lseq, hd, strides, strides, strides,
                                (Lseq * D, D), causal)
             pl.f(ops.attention_op(ad, (qkv, att, lse)))
-            x_mid = buf(tag + ".x_mid", (M, D))
+            x_mid = buf(tag + ".x_mid", (M, D), sdt)
             pl.f(ops.gemm_op(att, self.W(pre + nm["wo"]), x_mid, bias=self.P(pre + nm["bo"]), residual=x_in))
-            x_out = buf(tag + ".x_out", (M, D))
+            x_out = buf(tag + ".x_out", (M, D), sdt)
             # bias gradients that are column sums of a residual-stream gradient are produced by the LayerNorm backward
             # that writes that gradient: LN2-bwd -> out_proj bias of this block, LN1-bwd -> c_proj bias of the previous block
-            # (measured on B200: +1.15 ms of LN-backward time for 0.6 ms of removed colsum kernels -> off by default)
-            fuse_ln = bool(os.environ.get("SC_FUSE_LN_COLSUM"))
+            # (the column sums ride in registers of the LayerNorm backward, sc_layernorm_bwd `dx_colsum`; the first version with
+            # shared-memory accumulators cost more than the stand-alone colsum kernels it removed)
+            fuse_ln = not os.environ.get("SC_NO_FUSE_LN_COLSUM")
             grp_mlp = mlp(x_mid, x_out, dx, dxT, pre, nm, tag, eps, act, bo_grad=self.grads[pre + nm["bo"]] if fuse_ln else None)
             d_att, dqkv, d_ln = sbuf("d_att", (M, D), T), sbuf("dqkv", (M, 3 * D), T), sbuf("d_ln", (M, D), T)
             grp = linear_bwd(dxT, att, pre + nm["wo"], None if fuse_ln else pre + nm["bo"], dx=d_att)
@@ -468,7 +476,7 @@ class Engine:
             grp.append(ops.gemm_op(d_v, self.vdense, d_xin, trans_b=True, accumulate=True))
             grp.append(ops.gemm_op(d_kfeat, xin, self.dkdense, trans_a=True, trans_b=True, accumulate=True, split_k=-1))
             grp.append(ops.gemm_op(d_v, xin, self.dvdense, trans_a=True, trans_b=True, accumulate=True, split_k=-1))
-            grp.append(ln_bwd(d_xin, xp, st_norm, s + "norm", d_xp, True))
+            grp.append(ln_bwd(d_xin, xp, st_norm, s + "norm", d_xp, False))      # first writer of d_xp (this group runs first)
             grp.append(ln_bwd(d_qf, q2, st_cross, s + "cross_ln", dq, False, dqT))
             pl.b(grp)
             return sx, d_sx, idx
@@ -500,11 +508,11 @@ class Engine:
         eot = buf("t.eot", (B,), i32)
         pl.f(ops.text_embed_op(ids, self.P("clip.token_embedding.weight"), self.P("clip.positional_embedding"), xt, eot, B,
                                self.Tctx, W_))
-        dxt = buf("t.dx", (Mt, W_), zero=True)
+        dxt = buf("t.dx", (Mt, W_), zero=True)          # fp32 landing buffer of the EOT-row scatter; the blocks use dxtT only
         dxtT = tcopy("t.dxT", dxt)
         hd_ = None
         for i in range(self.text_layers):
-            xt, hd_ = block(xt, dxt, dxtT, f"clip.transformer.resblocks.{i}.", CLIP_BLOCK, f"t{i}", B, self.Tctx, self.Ht, True,
+            xt, hd_ = block(xt, dxtT, dxtT, f"clip.transformer.resblocks.{i}.", CLIP_BLOCK, f"t{i}", B, self.Tctx, self.Ht, True,
                             prev=hd_)
         xe = buf("t.xe", (B, W_))
         pl.f(ops.gather_rows_op(xt, eot, xe))
@@ -529,12 +537,10 @@ class Engine:
         pl.f("wait_image")        # the image H2D copy runs on a side stream underneath the text tower
         xv = vision_stem("v.stem", self.Lp, None)
         Mv = B * self.Lp
-        dxv = buf("v.dx", (Mv, D), zero=True)          # gradient of the layers0 stream (many contributors)
-        dxvT = tcopy("v.dxT", dxv)
+        dxv = buf("v.dx", (Mv, D), T)          # gradient of the layers0 stream; first written (not accumulated) by semantic()
         hd_ = None
         for i in range(self.fsl):
-            xv, hd_ = block(xv, dxv, dxvT, f"{t_}layers0.{i}.", CLIP_BLOCK, f"v{i}", B, self.Lp, self.Hv, prev=hd_)
-        pl.b(sync_T(dxv, dxvT))        # semantic backward accumulated into dxv; refresh the twin
+            xv, hd_ = block(xv, dxv, dxv, f"{t_}layers0.{i}.", CLIP_BLOCK, f"v{i}", B, self.Lp, self.Hv, prev=hd_)
         d_hard_kl = buf("v.d_hard_kl", (B, G, self.Lp)) if self.use_kl else None
         sx, d_sx, idx_main = semantic(xv, dxv, u1, forced_main, d_hard_kl, "v.sem", B, self.Lp)
         if self.use_kl:
@@ -617,12 +623,10 @@ class Engine:
             pl.f(ops.mae_mask_op(u2, ids_restore, ids_keep, mask, pidx, B, L1, keep))
             xm = vision_stem("m.stem", Lm, pidx)
             Mm = B * Lm
-            dxm = buf("m.dx", (Mm, D), zero=True)
-            dxmT = tcopy("m.dxT", dxm)
+            dxm = buf("m.dx", (Mm, D), T)
             hd_ = None
             for i in range(self.fsl):
-                xm, hd_ = block(xm, dxm, dxmT, f"{t_}layers0.{i}.", CLIP_BLOCK, f"m{i}", B, Lm, self.Hv, prev=hd_)
-            pl.b(sync_T(dxm, dxmT))
+                xm, hd_ = block(xm, dxm, dxm, f"{t_}layers0.{i}.", CLIP_BLOCK, f"m{i}", B, Lm, self.Hv, prev=hd_)
             d_hard_rec = buf("m.d_hard_rec", (B, G, Lm))
             sxm, d_sxm, idx_mae = semantic(xm, dxm, u3, forced_mae, d_hard_rec, "m.sem", B, Lm)
             r = t_ + "reconstruct_layer2.rec_proj_a.a_fc."

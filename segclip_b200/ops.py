@@ -207,7 +207,8 @@ def text_embed_op(ids, tok, pos, out, eot_rows, B, T, W):
 
 
 def gather_rows_op(src, idx, out):
-    return Op("sc_gather_rows", (src.data_ptr(), idx.data_ptr(), out.data_ptr(), out.shape[0], out.shape[1]), (src, idx, out))
+    assert out.dtype == torch.float32
+    return Op("sc_gather_rows", (src.data_ptr(), L.dt(src), idx.data_ptr(), out.data_ptr(), out.shape[0], out.shape[1]), (src, idx, out))
 
 
 def scatter_rows_op(src, idx, out):

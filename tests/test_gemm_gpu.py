@@ -20,12 +20,12 @@ def _ref(A, B, ta, tb, bias, rowbias, ridx, rmod, act, residual, alpha):
     elif act == 2:
         v = torch.nn.functional.gelu(v)
     if residual is not None:
-        v = v + residual
+        v = v + residual.float()
     return v, pre
 
 
 def _run(M, N, K, dtype, ta=False, tb=False, bias=False, rowbias=0, ridx=False, act=0, residual=False,
-         c_dtype=torch.float32, c2=None, accumulate=False, split_k=0, alpha=1.0, force_simt=False, seed=0):
+         c_dtype=torch.float32, c2=None, accumulate=False, split_k=0, alpha=1.0, force_simt=False, seed=0, res_dtype=torch.float32):
     from segclip_b200 import ops
     g = torch.Generator(device="cuda").manual_seed(seed)
     dev = "cuda"
@@ -34,7 +34,7 @@ def _run(M, N, K, dtype, ta=False, tb=False, bias=False, rowbias=0, ridx=False, 
     bias_t = torch.randn(N, device=dev, generator=g) if bias else None
     rb = torch.randn(rowbias, N, device=dev, generator=g) if rowbias else None
     ridx_t = torch.randint(0, rowbias, (M,), device=dev, generator=g, dtype=torch.int32) if (ridx and rowbias) else None
-    res = torch.randn(M, N, device=dev, generator=g) if residual else None
+    res = torch.randn(M, N, device=dev, generator=g).to(res_dtype) if residual else None
     C0 = torch.randn(M, N, device=dev, generator=g) if accumulate else None
     C = C0.clone() if accumulate else torch.full((M, N), float("nan"), device=dev, dtype=c_dtype)
     C2 = torch.full((M, N), float("nan"), device=dev, dtype=c2) if c2 is not None else None
@@ -180,3 +180,61 @@ def test_tc_plain_fp32_output_and_accumulate(M, N, K):
     _run(M, N, K, torch.bfloat16, tb=True)                          # NT, fp32 out
     _run(M, N, K, torch.bfloat16, tb=True, accumulate=True)         # NT, C += (old C prefetched)
     _run(M, N, K, torch.bfloat16, accumulate=True)                  # NN accumulate: generic path
+
+
+@pytest.mark.parametrize("M,N,K", [(1576, 768, 768), (4100, 768, 3072), (600, 512, 2048), (392, 768, 768), (154, 512, 512)])
+def test_tc_bf16_residual_stream_epilogue(M, N, K):
+    """out_proj / c_proj forward with the bf16 residual stream: C(bf16) = A B^T + bias + residual(bf16).  M >= 512 runs the
+    2-CTA kernel (residual tile TMA-loaded into the staging box its result is TMA-stored from, ragged last row tile
+    included), smaller M the 1-CTA kernel's generic epilogue."""
+    from segclip_b200 import _lib
+    k0 = _lib.kernel_launches()
+    _run(M, N, K, torch.bfloat16, bias=True, residual=True, c_dtype=torch.bfloat16, res_dtype=torch.bfloat16)
+    k1 = _lib.kernel_launches()
+    assert (k1["gemm_tc2"] - k0["gemm_tc2"] == 1) == (M >= 512), (k0, k1)
+
+
+def test_tc2_residual_epilogue_in_place_and_guard_band():
+    """The residual may alias the output (x += f(x) in place is not used by the engine, but the tile is read before it is
+    written); rows past M must stay untouched."""
+    from segclip_b200 import ops
+    torch.manual_seed(1)
+    M, N, K = 1000, 768, 256
+    A = torch.randn(M, K, device="cuda").bfloat16()
+    B = (torch.randn(N, K, device="cuda") * 0.1).bfloat16()
+    bias = torch.randn(N, device="cuda")
+    res = torch.randn(M, N, device="cuda").bfloat16()
+    big = torch.full((M + 40, N), 7.0, device="cuda", dtype=torch.bfloat16)
+    C = big[:M]
+    ops.gemm(A, B, C, bias=bias, residual=res)
+    torch.cuda.synchronize()
+    ref = A.float() @ B.float().t() + bias + res.float()
+    assert float((C.float() - ref).abs().max() / ref.abs().max()) < 1e-2
+    assert bool((big[M:] == 7.0).all())
+
+
+@pytest.mark.parametrize("M,N,K", [(1576, 768, 768), (4100, 512, 2048), (1000, 768, 3072), (50176, 768, 768)])
+def test_tc2_fp32_residual_stream_epilogue(M, N, K):
+    """out_proj / c_proj forward of the 2-CTA kernel: C(fp32) = A B^T + bias + residual(fp32), residual in and result out
+    through the TMA (two 4 KB fp32 boxes per epilogue warp, reloaded inside the tile), ragged last row tile included."""
+    from segclip_b200 import _lib
+    k0 = _lib.kernel_launches()
+    _run(M, N, K, torch.bfloat16, bias=True, residual=True)
+    assert _lib.kernel_launches()["gemm_tc2"] - k0["gemm_tc2"] == 1
+
+
+def test_tc2_fp32_residual_guard_band():
+    from segclip_b200 import ops
+    torch.manual_seed(2)
+    M, N, K = 1000, 768, 256
+    A = torch.randn(M, K, device="cuda").bfloat16()
+    B = (torch.randn(N, K, device="cuda") * 0.1).bfloat16()
+    bias = torch.randn(N, device="cuda")
+    res = torch.randn(M, N, device="cuda")
+    big = torch.full((M + 40, N), 7.0, device="cuda")
+    C = big[:M]
+    ops.gemm(A, B, C, bias=bias, residual=res)
+    torch.cuda.synchronize()
+    ref = A.float() @ B.float().t() + bias + res
+    assert float((C - ref).abs().max() / ref.abs().max()) < 2e-4
+    assert bool((big[M:] == 7.0).all())

@@ -14,7 +14,8 @@ DEV = "cuda"
 
 
 def _rel(a, b):
-    return float((a.float().cpu() - b.float().cpu()).abs().max() / (b.abs().max() + 1e-12))
+    a, b = a.float().cpu(), b.float().cpu()
+    return float((a - b).abs().max() / (b.abs().max() + 1e-12))
 
 
 @pytest.mark.parametrize("D", [64, 384, 768, 1024])
@@ -45,6 +46,38 @@ def test_layernorm_fwd_bwd(D, dtype):
     assert _rel(dx, base + xr.grad) < 1e-4
     assert _rel(dxc, base + xr.grad) < 1e-2
     assert _rel(dg, gr.grad) < 1e-4 and _rel(db, br.grad) < 1e-4
+
+
+@pytest.mark.parametrize("D", [512, 768, 1024, 384, 132])
+def test_layernorm_bwd_bf16_gradient_stream_with_colsum(D):
+    """The production configuration of the big streams: dy bf16, x fp32, the gradient stream dx accumulated IN PLACE in
+    bf16 (no fp32 copy), dgamma / dbeta and the column sums of the final dx (bias gradient of the residual branch's Linear)
+    from register accumulators.  D = 132 is not a multiple of 8 -> the shared-memory fallback kernel."""
+    from segclip_b200 import ops
+    torch.manual_seed(D)
+    rows = 1003
+    x = (torch.randn(rows, D) * 2 + 0.5).to(DEV)
+    g, b = torch.randn(D, device=DEV), torch.randn(D, device=DEV)
+    dy = torch.randn(rows, D, device=DEV).bfloat16()
+    base = torch.randn(rows, D, device=DEV).bfloat16()
+    xr = x.clone().requires_grad_(True)
+    gr, br = g.clone().requires_grad_(True), b.clone().requires_grad_(True)
+    F.layer_norm(xr, (D,), gr, br, 1e-5).backward(dy.float())
+    want = base.float() + xr.grad
+    y = torch.empty(rows, D, device=DEV, dtype=torch.bfloat16)
+    mean, rstd = torch.empty(rows, device=DEV), torch.empty(rows, device=DEV)
+    ops.layernorm_op(x, g, b, y, 1e-5, mean, rstd)()
+    dx = base.clone()
+    dg, db, cs = torch.zeros(D, device=DEV), torch.zeros(D, device=DEV), torch.zeros(D, device=DEV)
+    ops.layernorm_bwd_op(dy, x, mean, rstd, g, dx, True, None, dg, db, dx_colsum=cs)()
+    torch.cuda.synchronize()
+    assert _rel(dx, want) < 1e-2
+    assert _rel(dg, gr.grad) < 1e-4 and _rel(db, br.grad) < 1e-4
+    assert _rel(cs, want.sum(0)) < 1e-4                      # summed before the bf16 rounding of the store
+    # not accumulating, no parameter gradients (cross-attention K/V side): plain overwrite
+    dx2 = torch.full_like(dx, float("nan"))
+    ops.layernorm_bwd_op(dy, x, mean, rstd, g, dx2, False)()
+    assert _rel(dx2, xr.grad) < 1e-2
 
 
 def test_layernorm_row_remap_into_concat_buffer():

@@ -22,6 +22,8 @@ SHAPES = [  # name, M, N, K, ta, tb, kwargs
     ("text c_fc fwd", 19712, 2048, 512, False, False, dict(bias=True, act=1, c2=True, out=torch.bfloat16)),
     ("text c_proj dgrad*", 19712, 2048, 512, False, True, dict(out=torch.bfloat16, aux=True)),
     ("text c_proj fwd", 19712, 512, 2048, False, False, dict(bias=True, residual=True, out=torch.float32)),
+    ("text out_proj fwd", 19712, 512, 512, False, False, dict(bias=True, residual=True, out=torch.float32)),
+    ("c_proj dgrad*+cs", 50176, 3072, 768, False, True, dict(out=torch.bfloat16, aux=True, colsum=True)),
     ("plain 8192^3", 8192, 8192, 8192, False, False, dict(out=torch.bfloat16)),
 ]
 
@@ -39,8 +41,9 @@ def main():
         res = torch.randn(M, N, device=dev) if kw.get("residual") else None
         C2 = torch.empty(M, N, device=dev, dtype=kw["out"]) if kw.get("c2") else None
         aux = torch.randn(M, N, device=dev).bfloat16() if kw.get("aux") else None
+        cs = torch.zeros(N, device=dev) if kw.get("colsum") else None
         op = ops.gemm_op(A, B, C, trans_a=ta, trans_b=tb, bias=bias, residual=res, act=kw.get("act", 0), C2=C2,
-                         mul_aux=aux, mul_aux_act=1 if aux is not None else 0,
+                         mul_aux=aux, mul_aux_act=1 if aux is not None else 0, colsum_out=cs,
                          accumulate=kw.get("acc", False), split_k=-1 if kw.get("acc") else 0)
         for _ in range(3):
             op()

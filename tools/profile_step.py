@@ -41,9 +41,10 @@ def main():
     ap.add_argument("--heads", action="store_true")
     ap.add_argument("--ncu", action="store_true")
     ap.add_argument("--top", type=int, default=40)
+    ap.add_argument("--model", default="vitb16", choices=["vitb16", "vitl14"])
     args = ap.parse_args()
     dev = torch.device("cuda", 0)
-    cfg = config.vit_b16(use_mae=args.heads, use_kl=args.heads)
+    cfg = (config.vit_l14 if args.model == "vitl14" else config.vit_b16)(use_mae=args.heads, use_kl=args.heads)
     tc = argparse.Namespace(local_rank=0, rank=0, world_size=1, first_stage_layer=10, use_vision_mae_recon=args.heads,
                             use_seglabel=args.heads, precision="bf16")
     torch.manual_seed(0)
@@ -90,7 +91,7 @@ def main():
         k = (phase, name)
         c, t = agg.get(k, (0, 0.0))
         agg[k] = (c + 1, t + ms)
-    print("total %.2f ms over %d native calls (batch %d, heads=%s)" % (tot, len(recs), args.batch, args.heads))
+    print("total %.2f ms over %d native calls (%s, batch %d, heads=%s)" % (tot, len(recs), args.model, args.batch, args.heads))
     byname = collections.Counter()
     for (phase, name), (c, t) in agg.items():
         byname[name.split(" ")[0] + ":" + phase] += t
