@@ -407,6 +407,18 @@ int sc_grad_sqnorm_multi(const sc_opt_item* items_dev, int n_items, int64_t tota
 int sc_adamw_multi(const sc_opt_item* items_dev, int n_items, int64_t total_blocks, const float* sqnorm, float max_norm,
                    float beta1, float beta2, float eps, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Gradient mean over NVSwitch multicast (replaces the DDP bucket all-reduce,
+ * main_task_align.py:251-252).  `multicast_ptr` is the NVLS multicast address of `count` fp32 values that live at the
+ * same offset of a symmetric buffer on every rank; after the call every replica holds scale * sum over ranks.
+ * peer_flags_dev: device array of `world` pointers, entry t = rank t's flag array (uint32 [SC_NVLS_MAX_BLOCKS * world],
+ * zero-initialised, peer-mapped).  `epoch` must advance by 2 per call, identically on every rank.  *err_flag is set to 1
+ * if a peer does not arrive within timeout_ms (the kernel then returns instead of hanging).
+ */
+#define SC_NVLS_MAX_BLOCKS 64
+int sc_nvls_allreduce(void* multicast_ptr, int64_t count, float scale, int rank, int world, void* const* peer_flags_dev,
+                      uint32_t epoch, int blocks, int64_t timeout_ms, int32_t* err_flag, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

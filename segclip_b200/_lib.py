@@ -83,6 +83,9 @@ def parse_header(path=HEADER_PATH):
 
 
 STRUCTS, FUNCS = parse_header()
+# integer #defines of the header (SC_NVLS_MAX_BLOCKS, ...)
+DEFINES = {m.group(1): int(m.group(2)) for m in re.finditer(r"#define\s+(SC_\w+)\s+\(?(-?\d+)\)?\s", open(HEADER_PATH).read())}
+SC_NVLS_MAX_BLOCKS = DEFINES["SC_NVLS_MAX_BLOCKS"]
 GemmDesc = STRUCTS["sc_gemm_desc"]
 LnDesc = STRUCTS["sc_ln_desc"]
 LnBwdDesc = STRUCTS["sc_ln_bwd_desc"]

@@ -412,6 +412,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
             tmem_ld32_nowait(tmem + lane_off + TM_ST + cg * 32, s);
             tmem_ld32_nowait(tmem + lane_off + TM_DPT + cg * 32, dp);
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            if (warp == 0) TRACE(1, 18);
             const int row_lo = qt * TILE + quarter * 32;       // the warp's first query
             const bool full = row_lo + 31 < L && key0 + 31 < L && (!CAUSAL || key0 + 31 <= row_lo);   // warp-uniform
             if (full) {                                        // interior block: no masks

@@ -103,6 +103,7 @@ class Engine:
         self.gather = None        # multi-GPU embedding exchange (segclip_b200.p2p), set by the module
         self.sync_group = None    # native gradient all-reduce (enable_grad_sync)
         self.sync_world = 1
+        self.nvls = None          # NVSwitch-multicast transport of the gradient buckets (segclip_b200.allreduce)
 
     # ------------------------------------------------------------------ parameters
     def _setup_params(self):
@@ -152,7 +153,13 @@ class Engine:
             offs.append(tot)
             tot += (s + 3) // 4 * 4          # keep every view 16-byte aligned
         if getattr(self, "gflat", None) is None or self.gflat.numel() != tot:
-            self.gflat = torch.zeros(tot, device=self.dev, dtype=torch.float32)
+            self.gflat = None
+            if getattr(self, "nvls", None) is not None:          # symmetric memory bound to an NVSwitch multicast object
+                self.gflat = self.nvls.alloc(tot)
+                if self.gflat is None:
+                    self.nvls = None
+            if self.gflat is None:
+                self.gflat = torch.zeros(tot, device=self.dev, dtype=torch.float32)
         self.goffs = dict(zip(names, offs))
         self.gsizes = dict(zip(names, sizes))
         self.grads = {n: self.gflat[o:o + s].view(self.params[n].shape) for n, o, s in zip(names, offs, sizes)}
@@ -173,6 +180,12 @@ class Engine:
         del probe
         order = sorted(self.grad_names, key=lambda n: (last[n], self.goffs[n]))
         self._grad_last_op = last
+        # transport of the bucket reductions: the library's NVLS multimem kernel when the GPUs share an NVSwitch multicast
+        # domain, else (or with SEGCLIP_GRAD_SYNC=nccl: the comparator) NCCL all-reduce
+        from .allreduce import NvlsGradSync
+        self.nvls = NvlsGradSync.create(group, self.dev) if self.sync_world > 1 else None
+        if self.nvls is not None:
+            self.gflat = None          # re-allocate as symmetric memory
         self._layout_grads(order)
         # buckets over the new order
         bucket_mb = bucket_mb or float(os.environ.get("SEGCLIP_BUCKET_MB", "48"))
@@ -847,11 +860,20 @@ class Engine:
         pl = self.plan(B)
         st = L.stream()
         works = []
-        if pl.bucket_after:
-            import torch.distributed as dist
-            for k in pl.bucket_after.get(-1, []):          # parameters nobody writes (stay zero)
-                s, e_, _ = self.buckets[k]
+        nv = self.nvls
+        cur = torch.cuda.current_stream(self.dev) if pl.bucket_after else None
+
+        def reduce_bucket(k):
+            s, e_, _ = self.buckets[k]
+            if nv is not None:         # mean over ranks by the NVLS kernel on its own stream, behind everything issued so far
+                nv.all_reduce(s, e_, cur)
+            else:
+                import torch.distributed as dist
                 works.append(dist.all_reduce(self.gflat[s:e_], group=self.sync_group, async_op=True))
+
+        if pl.bucket_after:
+            for k in pl.bucket_after.get(-1, []):          # parameters nobody writes (stay zero)
+                reduce_bucket(k)
         for i, op in enumerate(pl.bwd):
             if isinstance(op, str):
                 self._collective(op, pl)
@@ -859,10 +881,11 @@ class Engine:
                 op(st)
             if pl.bucket_after and i in pl.bucket_after:
                 for k in pl.bucket_after[i]:
-                    s, e_, _ = self.buckets[k]
-                    works.append(dist.all_reduce(self.gflat[s:e_], group=self.sync_group, async_op=True))
+                    reduce_bucket(k)
         for w in works:
             w.wait()               # stream-level wait, the host does not block
+        if nv is not None and pl.bucket_after:
+            nv.join(cur)
         return self.gflat
 
     def profile_gemm(self, B):

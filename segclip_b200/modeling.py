@@ -244,8 +244,8 @@ class _NativeStep(torch.autograd.Function):
         gflat = eng.backward(ctx.B)
         out = torch.empty_like(gflat)
         scale = gout.detach().to(torch.float32).contiguous().view(1)
-        if eng.sync_world > 1:
-            scale = scale / eng.sync_world          # mean over ranks, folded into the hand-over copy
+        if eng.sync_world > 1 and eng.nvls is None:
+            scale = scale / eng.sync_world          # mean over ranks, folded into the hand-over copy (the NVLS kernel scales itself)
         ops.convert_op(gflat, out, scale)()          # grad * grad_output, read on the device
         grads = []
         for name, p in owner._active_items:

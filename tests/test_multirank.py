@@ -53,6 +53,10 @@ def _gpu_worker(rank, world, port, mode, q):
     os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
     os.environ["SEGCLIP_EXCHANGE"] = "nccl" if mode == "nccl" else "p2p"
     os.environ["SEGCLIP_P2P_TIMEOUT_S"] = "60"       # a protocol bug must end the test, not hang the box
+    if mode == "native_nccl":
+        os.environ["SEGCLIP_GRAD_SYNC"] = "nccl"     # comparator transport of the gradient buckets
+    elif mode == "native_nvls":
+        os.environ["SEGCLIP_GRAD_SYNC"] = "nvls"     # the library's multimem kernel; fails loudly without NVSwitch multicast
     torch.cuda.set_device(rank)
     dev = torch.device("cuda", rank)
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
@@ -69,7 +73,7 @@ def _gpu_worker(rank, world, port, mode, q):
     model.load_state_dict(so.init_params(cfg, seed=g["param_seed"]), strict=False)
     model = model.to(dev).train()
     model.attach_exchange(EmbeddingExchange(dist.group.WORLD, dev))
-    if mode == "native":                    # gradient mean inside the native backward (overlapped bucketed all-reduce)
+    if mode.startswith("native"):           # gradient mean inside the native backward (overlapped bucket reductions)
         model.enable_native_grad_sync(dist.group.WORLD)
     batch, noise = so.make_batch(cfg, g["batch"], seed=g["batch_seed"], rank=rank)
     model.inject_noise({k: v.to(dev) for k, v in noise.items()})
@@ -93,18 +97,22 @@ def _gpu_worker(rank, world, port, mode, q):
     for n, p in model.named_parameters():
         if p.grad is not None:
             gr = p.grad.detach().clone()
-            if mode not in ("native",):
+            if not mode.startswith("native"):
                 dist.all_reduce(gr)
                 gr = gr / world
             grads[n] = gr.cpu()
     bad = compare_grads(grads, g["grads"], tol=1e-3, skip=FROZEN_STEM) if rank == 0 else []
+    if mode == "native_nvls":
+        assert model._engine.nvls is not None
+        model._engine.nvls.check()
     q.put((rank, losses, g["loss"][rank], bad[:5]))
     dist.barrier()
     dist.destroy_process_group()
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("world,mode", [(2, "p2p"), (2, "nccl"), (2, "native"), (2, "p2p_eval"), (8, "native")])
+@pytest.mark.parametrize("world,mode", [(2, "p2p"), (2, "nccl"), (2, "native"), (2, "native_nccl"), (2, "native_nvls"),
+                                        (2, "p2p_eval"), (8, "native"), (8, "native_nvls")])
 def test_ranks_match_reference_fixture(world, mode):
     """W ranks of the real CUDA path against the W-rank fixture of the unmodified reference (W gloo processes:
     diffdist all-gather + DDP gradient mean).  W = 8 checks the epoch / consumed flag protocol at the full fan-out of the box."""
@@ -112,7 +120,7 @@ def test_ranks_match_reference_fixture(world, mode):
         pytest.skip("needs %d GPUs (gpurun --gpus %d)" % (world, world))
     ctx = mp.get_context("spawn")
     q = ctx.SimpleQueue()
-    port = {"p2p": 29571, "nccl": 29573, "native": 29575, "p2p_eval": 29577}[mode] + 20 * (world == 8)
+    port = {"p2p": 29571, "nccl": 29573, "native": 29575, "p2p_eval": 29577, "native_nccl": 29579, "native_nvls": 29581}[mode] + 20 * (world == 8)
     procs = [ctx.Process(target=_gpu_worker, args=(r, world, port, mode, q)) for r in range(world)]
     for p in procs:
         p.start()
@@ -123,3 +131,55 @@ def test_ranks_match_reference_fixture(world, mode):
         for l in losses:
             assert abs(l - want) <= 1e-3 * abs(want), (rank, losses, want)
         assert not bad, bad
+
+
+def _nvls_worker(rank, world, port, q):
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    os.environ["SEGCLIP_GRAD_SYNC"] = "nvls"
+    os.environ["SEGCLIP_P2P_TIMEOUT_S"] = "60"
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    from segclip_b200.allreduce import NvlsGradSync
+    nv = NvlsGradSync.create(dist.group.WORLD, dev)
+    n = 3 * 1024 * 1024 + 8
+    buf = nv.alloc(n)
+    assert buf is not None, "no NVSwitch multicast mapping"
+    g = torch.Generator(device=dev).manual_seed(100 + rank)
+    ok = True
+    cur = torch.cuda.current_stream(dev)
+    for (lo, hi) in ((0, n), (4, 1028), (1024 * 1024 + 4, n - 4), (8, 12)):      # whole buffer, tiny, unaligned-to-slices ranges
+        buf.copy_(torch.randn(n, device=dev, generator=g))
+        want = buf.clone()
+        dist.all_reduce(want[lo:hi])
+        want[lo:hi] /= world
+        torch.cuda.synchronize()
+        dist.barrier()
+        nv.all_reduce(lo, hi, cur)
+        nv.join(cur)
+        torch.cuda.synchronize()
+        nv.check()
+        err = float((buf - want).abs().max())
+        ok = ok and err <= 1e-5 * (1 + float(want.abs().max()))
+        dist.barrier()
+    q.put((rank, ok))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("world", [2, 8])
+def test_nvls_allreduce_matches_nccl(world):
+    """sc_nvls_allreduce (multimem.ld_reduce / multimem.st two-shot kernel on the symmetric gradient buffer) against NCCL's
+    all-reduce on sub-ranges of the buffer; values outside the range must stay untouched."""
+    if torch.cuda.device_count() < world:
+        pytest.skip("needs %d GPUs" % world)
+    ctx = mp.get_context("spawn")
+    q = ctx.SimpleQueue()
+    procs = [ctx.Process(target=_nvls_worker, args=(r, world, 29641 + world, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = dict(q.get() for _ in range(world))
+    for p in procs:
+        p.join(120)
+    assert all(res.values()), res

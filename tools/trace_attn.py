@@ -34,7 +34,7 @@ lib.sc_debug_attn_trace(buf, n)          # drop the warm-up trace
 lib.sc_debug_attn_trace(buf, n)
 names = {1: "item start", 2: "loads landed", 3: "SdP(0) issued", 4: "bar_p seen", 5: "next SdP issued / acc free", 6: "dVdKdQ issued",
          7: "last MMAs retired", 10: "soft: wait S", 11: "soft: S ready", 12: "soft: computed", 13: "soft: tiles free", 14: "soft: P arrived",
-         15: "soft: dkv ready", 16: "soft: dkv stored", 17: "soft: dq stored",
+         15: "soft: dkv ready", 16: "soft: dkv stored", 17: "soft: dq stored", 18: "soft: S/dP loaded from TMEM",
          20: "F item start", 21: "F QK landed", 22: "F S issued", 23: "F S done", 24: "F V+P ready", 25: "F PV issued", 26: "F O done",
          27: "F O read out", 30: "Fs wait S", 31: "Fs S ready", 32: "Fs pass1 done", 33: "Fs P arrived", 34: "Fs O ready",
          35: "Fs O loaded", 36: "Fs stored"}
