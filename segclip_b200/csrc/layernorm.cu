@@ -317,6 +317,208 @@ int launch_bwd8(const sc_ln_bwd_desc& d, cudaStream_t st) {
   return SC_OK;
 }
 
+// ---- bulk-copy-prefetched backward (the production kernel for D % 8 == 0) -------------------------------------------
+// ln_bwd8_kernel above keeps a whole row per warp in registers: with 12 warps per SM only 12 rows (~90 KB) are in flight
+// per SM and the kernel is bound by HBM LATENCY (4.0 TB/s measured, 10 B per element).  Here every warp owns a ring of
+// LNT_STAGES row slots in shared memory that is filled by cp.async.bulk (the TMA's 1-D copy: x row, dy row, old dx row,
+// one mbarrier per slot) up to three rows ahead: 36 rows (216 KB) in flight per SM at no register cost.  The warp makes
+// two passes over its slot (statistics, then outputs), so only the three accumulator sets live in registers.
+constexpr int LNT_WARPS = 6;      // 2 CTAs x 6 warps x 3 slots of 6 KB (D = 768) fill the SM's shared memory
+constexpr int LNT_STAGES = 3;
+
+SC_DEVINL uint32_t lnt_smem(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+SC_DEVINL void lnt_bulk(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
+               "r"(bytes), "r"(bar)
+               : "memory");
+}
+SC_DEVINL void lnt_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done = 0;
+  while (!done) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+  }
+}
+template <typename T> SC_DEVINL void lds8(uint32_t a, float (&v)[8]);
+template <> SC_DEVINL void lds8<float>(uint32_t a, float (&v)[8]) {
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]) : "r"(a));
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7]) : "r"(a + 16));
+}
+template <> SC_DEVINL void lds8<bf16>(uint32_t a, float (&v)[8]) {
+  uint32_t w[4];
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]) : "r"(a));
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float2 f = __bfloat1622float2(*(const __nv_bfloat162*)&w[i]);
+    v[2 * i] = f.x;
+    v[2 * i + 1] = f.y;
+  }
+}
+
+template <typename TDY, typename TX, typename TDX, int NV8, bool CS>
+__global__ void __launch_bounds__(LNT_WARPS * 32, 2) ln_bwd_tma_kernel(sc_ln_bwd_desc d) {
+  extern __shared__ __align__(128) uint8_t lsm[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int D = d.D, D8 = D >> 3;
+  const bool want_param = d.dgamma != nullptr;
+  const bool acc = d.dx && d.accumulate_dx;
+  const uint32_t xb = D * sizeof(TX), yb = D * sizeof(TDY), ob = acc ? D * (uint32_t)sizeof(TDX) : 0u;
+  const uint32_t slot_bytes = xb + yb + ob;                  // multiples of 16 (D % 8 == 0)
+  // layout: gamma [D] | per warp: LNT_STAGES slots | mbarriers; the cross-warp reduction at the end reuses the slots
+  float* gam = (float*)lsm;
+  uint8_t* ring = lsm + D * 4 + (size_t)warp * LNT_STAGES * slot_bytes;
+  uint64_t* bars = (uint64_t*)(lsm + D * 4 + (size_t)LNT_WARPS * LNT_STAGES * slot_bytes) + warp * LNT_STAGES;
+  for (int i = threadIdx.x; i < D; i += LNT_WARPS * 32) gam[i] = d.gamma[i];
+  if (lane == 0) {
+    for (int s = 0; s < LNT_STAGES; ++s)
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(lnt_smem(&bars[s])) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  const long stride = (long)gridDim.x * LNT_WARPS;
+  const long row0 = (long)blockIdx.x * LNT_WARPS + warp;
+  auto issue = [&](long row, int s) {                        // lane 0 only
+    const uint32_t bar = lnt_smem(&bars[s]);
+    const uint32_t dst = lnt_smem(ring + (size_t)s * slot_bytes);
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(slot_bytes) : "memory");
+    lnt_bulk(dst, (const TX*)d.x + row * D, xb, bar);
+    lnt_bulk(dst + xb, (const TDY*)d.dy + remap_row(row, d.in_group, d.out_group, d.out_off) * D, yb, bar);
+    if (acc) lnt_bulk(dst + xb + yb, (const TDX*)d.dx + row * D, ob, bar);
+  };
+  if (lane == 0) {
+    for (int s = 0; s < LNT_STAGES; ++s)
+      if (row0 + s * stride < d.rows) issue(row0 + s * stride, s);
+  }
+  float dg[NV8][8], db[NV8][8], cs[CS ? NV8 : 1][8];
+#pragma unroll
+  for (int j = 0; j < NV8; ++j)
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      dg[j][k] = 0.f;
+      db[j][k] = 0.f;
+      if (CS) cs[j][k] = 0.f;
+    }
+  const uint32_t gbase = lnt_smem(gam);
+  int s = 0;
+  uint32_t phase = 0;
+  for (long row = row0; row < d.rows; row += stride) {
+    const float mean = d.mean[row], rstd = d.rstd[row];      // issued before the wait: overlaps the copy's flight
+    const uint32_t slot = lnt_smem(ring + (size_t)s * slot_bytes);
+    lnt_wait(lnt_smem(&bars[s]), phase);
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int j = 0; j < NV8; ++j) {
+      const int c8 = lane + 32 * j;
+      if (c8 < D8) {
+        float xv[8], dv[8], gm[8];
+        lds8<TX>(slot + c8 * 8 * (uint32_t)sizeof(TX), xv);
+        lds8<TDY>(slot + xb + c8 * 8 * (uint32_t)sizeof(TDY), dv);
+        lds8<float>(gbase + c8 * 32, gm);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const float xh = (xv[k] - mean) * rstd;
+          const float g = dv[k] * gm[k];
+          s1 += g;
+          s2 = fmaf(g, xh, s2);
+          dg[j][k] = fmaf(dv[k], xh, dg[j][k]);
+          db[j][k] += dv[k];
+        }
+      }
+    }
+    const float c1 = warp_sum(s1) / D, c2 = warp_sum(s2) / D;
+    if (d.dx) {
+      TDX* dx = (TDX*)d.dx + row * D;
+#pragma unroll
+      for (int j = 0; j < NV8; ++j) {
+        const int c8 = lane + 32 * j;
+        if (c8 < D8) {
+          float xv[8], dv[8], gm[8], o[8];
+          lds8<TX>(slot + c8 * 8 * (uint32_t)sizeof(TX), xv);
+          lds8<TDY>(slot + xb + c8 * 8 * (uint32_t)sizeof(TDY), dv);
+          lds8<float>(gbase + c8 * 32, gm);
+          if (acc) lds8<TDX>(slot + xb + yb + c8 * 8 * (uint32_t)sizeof(TDX), o);
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            const float xh = (xv[k] - mean) * rstd;
+            const float v = rstd * (dv[k] * gm[k] - c1 - xh * c2);
+            o[k] = acc ? o[k] + v : v;
+            if (CS) cs[j][k] += o[k];
+          }
+          st8<TDX>(dx + c8 * 8, o);
+          if (d.dx_copy_bf16) st8<bf16>((bf16*)d.dx_copy_bf16 + row * D + c8 * 8, o);
+        }
+      }
+    }
+    __syncwarp();                                            // every lane has read the slot
+    if (lane == 0 && row + LNT_STAGES * stride < d.rows) {
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      issue(row + LNT_STAGES * stride, s);
+    }
+    if (++s == LNT_STAGES) { s = 0; phase ^= 1; }
+  }
+  if (!want_param && !CS) return;
+  __syncthreads();                                           // all rings idle: reuse them as the reduction scratch
+  float* red = (float*)(lsm + D * 4);                        // [LNT_WARPS][D]
+#pragma unroll
+  for (int which = 0; which < (CS ? 3 : 2); ++which) {
+    float* dst = which == 0 ? d.dgamma : (which == 1 ? d.dbeta : d.dx_colsum);
+    if (dst == nullptr) continue;          // uniform
+#pragma unroll
+    for (int j = 0; j < NV8; ++j) {
+      const int c8 = lane + 32 * j;
+      if (c8 < D8) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) red[warp * D + c8 * 8 + k] = which == 0 ? dg[j][k] : (which == 1 ? db[j][k] : cs[CS ? j : 0][k]);
+      }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < D; i += LNT_WARPS * 32) {
+      float sum = 0.f;
+#pragma unroll
+      for (int w = 0; w < LNT_WARPS; ++w) sum += red[w * D + i];
+      atomicAdd(dst + i, sum);
+    }
+    __syncthreads();
+  }
+}
+
+template <typename TDY, typename TX, typename TDX>
+int launch_bwd_tma(const sc_ln_bwd_desc& d, cudaStream_t st) {
+  const int nv = ceil_div(d.D, 256);
+  const bool acc = d.dx && d.accumulate_dx;
+  const size_t slot = (size_t)d.D * (sizeof(TX) + sizeof(TDY) + (acc ? sizeof(TDX) : 0));
+  size_t smem = (size_t)d.D * 4 + LNT_WARPS * LNT_STAGES * slot + LNT_WARPS * LNT_STAGES * 8;
+  const size_t red = (size_t)d.D * 4 + (size_t)LNT_WARPS * d.D * 4;
+  if (smem < red) smem = red;
+  int per_sm = (int)((227 * 1024) / (smem + 1024));
+  if (per_sm > 2) per_sm = 2;
+  if (per_sm < 1) return SC_ERR_UNSUPPORTED;
+  long g = ceil_div(d.rows, LNT_WARPS);
+  const int grid = (int)(g < (long)per_sm * sc_num_sms() ? g : (long)per_sm * sc_num_sms());
+#define SC_LNT_CASE(NV_, CS_)                                                                                            \
+  {                                                                                                                      \
+    static sc_device_once once;                                                                                          \
+    if (once.first()) { cudaFuncSetAttribute(ln_bwd_tma_kernel<TDY, TX, TDX, NV_, CS_>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); once.done(); } \
+    ln_bwd_tma_kernel<TDY, TX, TDX, NV_, CS_><<<grid, LNT_WARPS * 32, smem, st>>>(d);                                    \
+  }
+#define SC_LNT_NV(NV_) if (d.dx_colsum) SC_LNT_CASE(NV_, true) else SC_LNT_CASE(NV_, false)
+  switch (nv) {
+    case 1: SC_LNT_NV(1); break;
+    case 2: SC_LNT_NV(2); break;
+    case 3: SC_LNT_NV(3); break;
+    default: SC_LNT_NV(4); break;
+  }
+#undef SC_LNT_NV
+#undef SC_LNT_CASE
+  SC_LAUNCH_CHECK();
+  return SC_OK;
+}
+
 template <typename TX, typename TY>
 int launch_fwd(const sc_ln_desc& d, cudaStream_t st) {
   const int nv = ceil_div(d.D, 128);
@@ -390,8 +592,26 @@ extern "C" int sc_layernorm_bwd(const sc_ln_bwd_desc* d, void* stream) {
   sc_count_launch(1);
   const int key = d->dy_dtype * 4 + d->x_dtype * 2 + d->dx_dtype;
   static const bool old_kernel = getenv("SC_LN_BWD_SMEM") != nullptr;      // A/B switch: shared-memory accumulator version
-  if (!old_kernel && d->D % 8 == 0 && d->D <= 1024 &&
-      ((uintptr_t)d->x & 15) == 0 && ((uintptr_t)d->dy & 15) == 0 && ((uintptr_t)d->dx & 15) == 0 && ((uintptr_t)d->gamma & 15) == 0) {
+  static const bool reg_kernel = getenv("SC_LN_BWD_REGS") != nullptr;      // A/B switch: whole row in registers, no prefetch ring
+  const bool vec8 = d->D % 8 == 0 && d->D <= 1024 && ((uintptr_t)d->x & 15) == 0 && ((uintptr_t)d->dy & 15) == 0 &&
+                    ((uintptr_t)d->dx & 15) == 0 && ((uintptr_t)d->gamma & 15) == 0;
+  // the prefetch ring pays off on long rows and many of them (measured: D = 768 x 50176 rows 5.0 vs 4.0 TB/s; D = 512 x 19712
+  // rows 3.7 vs 4.6 TB/s: too few rows per warp to amortise the prologue / final reduction)
+  if (!old_kernel && !reg_kernel && vec8 && d->D >= 640 && d->rows >= 16384) {
+    int rc = SC_ERR_UNSUPPORTED;
+    switch (key) {
+      case 0: rc = launch_bwd_tma<float, float, float>(*d, st); break;
+      case 1: rc = launch_bwd_tma<float, float, bf16>(*d, st); break;
+      case 2: rc = launch_bwd_tma<float, bf16, float>(*d, st); break;
+      case 3: rc = launch_bwd_tma<float, bf16, bf16>(*d, st); break;
+      case 4: rc = launch_bwd_tma<bf16, float, float>(*d, st); break;
+      case 5: rc = launch_bwd_tma<bf16, float, bf16>(*d, st); break;
+      case 6: rc = launch_bwd_tma<bf16, bf16, float>(*d, st); break;
+      case 7: rc = launch_bwd_tma<bf16, bf16, bf16>(*d, st); break;
+    }
+    if (rc != SC_ERR_UNSUPPORTED) return rc;
+  }
+  if (!old_kernel && vec8) {
     switch (key) {
       case 0: return launch_bwd8<float, float, float>(*d, st);
       case 1: return launch_bwd8<float, float, bf16>(*d, st);
