@@ -13,6 +13,8 @@
 //   dQ_qt += dS   K_kt          (A = dS^T tile read MN-major, B = K MN-major, N = 64) -> TMEM cols [384,448) / [448,512)
 // TMEM is used completely (512 columns).  Warps 0-7: softmax + epilogues (lane quarter = warp % 4, column half = warp / 4);
 // warp 16: MMA issue, warp 17: TMA producer (one elected lane each).
+#include <stdlib.h>
+
 #include "gemm_tc_common.cuh"
 
 namespace {
@@ -497,7 +499,8 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
 // loads run under the softmax / epilogue of the current item, and the two co-resident CTAs fill each other's bubbles.
 // L <= 256 means a whole score row fits in TMEM: no online-softmax rescaling.
 //   S = Q_tile K^T           (A, B from smem, K-major; N = L rounded up to 16)          -> TMEM cols [0, N)
-//   softmax warps (thread = row): pass 1 row max, pass 2 p = exp2(s c - m c), row sum; P is written back as packed bf16
+//   softmax warps (thread = row): ONE pass, p = exp2(s c - shift) with a lagging row maximum as shift (see the kernel), row
+//                            sum; P is written back as packed bf16
 //                            INTO TMEM over the consumed S columns [0, N/2)  (tcgen05.st)
 //   O = P V                  (A = P from TMEM, B = V from smem MN-major, N = 64)          -> TMEM cols [128, 192)
 //   epilogue: O / rowsum -> bf16 -> global; lse = m scale + ln(rowsum)
@@ -531,7 +534,7 @@ SC_DEVINL void tmem_st16(uint32_t taddr, const uint32_t* r) {
 template <bool CAUSAL>
 __global__ void __launch_bounds__(F_THREADS, 2)
 attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
-                   const __grid_constant__ CUtensorMap tmV, sc_attn_desc a) {
+                   const __grid_constant__ CUtensorMap tmV, sc_attn_desc a, int online) {
   extern __shared__ __align__(1024) uint8_t smem[];
   if ((smem_u32(smem) & 1023u) != 0u) __trap();
   const uint32_t sbase = smem_u32(smem);
@@ -757,9 +760,74 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     if (warp == 0) TRACE(1, 31);
     if (warp_live) {
       const int kmax = CAUSAL ? min(L, qi + 1) : L;          // this row sees keys [0, kmax)
+      float bufa[32], bufb[32];                                // named buffers: static register indexing
+      float s4[4] = {0.f, 0.f, 0.f, 0.f};
+      if (online) {
+        // ---- ONE pass over S (TMEM reads, ~64 B/clk/SM, are the floor of this kernel at head dim 64; two passes read every
+        // score twice).  The exponent shift is a LAGGING row maximum: it starts as the maximum of the first 32 keys and is
+        // raised only when a later chunk exceeds it by more than 2^8 in the exp2 domain; until then p = exp2(s c - shift)
+        // may reach 256, which bf16 / the fp32 row sum hold exactly as well as values <= 1 (softmax is shift invariant,
+        // O / rowsum and lse = shift + ln(rowsum) absorb it).  When the shift does move (rare; warp vote), the P chunks
+        // already written are re-read from TMEM, scaled by exp2(old - new) and written back.
+        float sh = -INFINITY;                                  // current shift, in units of s (not yet multiplied by c)
+        auto online_chunk = [&](float (&s)[32], float (&nxt)[32], int c0) {
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+          if (c0 + 32 < npad) tmem_ld32_nowait(tmem + lane_off + c0 + 32, nxt);
+          const bool edge = c0 + 32 > kmax;
+          float cm4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+          if (!edge) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) cm4[j & 3] = fmaxf(cm4[j & 3], s[j]);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              s[j] = c0 + j < kmax ? s[j] : -INFINITY;       // masked keys: exp2(-inf) = 0
+              cm4[j & 3] = fmaxf(cm4[j & 3], s[j]);
+            }
+          }
+          const float cm = fmaxf(fmaxf(cm4[0], cm4[1]), fmaxf(cm4[2], cm4[3]));
+          const bool raise = (cm - sh) * c > 8.0f;             // also true for the first live chunk (sh = -inf)
+          if (__any_sync(0xffffffffu, raise)) {
+            const float nsh = raise ? cm : sh;
+            if (c0 > 0) {                                      // rescale what this row has already written
+              const float f = (sh == -INFINITY) ? 0.f : ex2f((sh - nsh) * c);     // 1 for rows whose shift stays
+              asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+              for (int pc = 0; pc < c0; pc += 32) {
+                float q[16];
+                tmem_ld16(tmem + lane_off + (pc >> 1), q);
+                uint32_t w[16];
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                  const uint32_t u = __float_as_uint(q[j]);
+                  const float2 x = __bfloat1622float2(*(const __nv_bfloat162*)&u);
+                  w[j] = pack_bf16(x.x * f, x.y * f);
+                }
+                tmem_st16(tmem + lane_off + (pc >> 1), w);
+              }
+#pragma unroll
+              for (int k = 0; k < 4; ++k) s4[k] *= f;
+            }
+            sh = nsh;
+          }
+          const float shc = (sh == -INFINITY) ? 0.f : sh * c;
+          uint32_t pk[16];
+#pragma unroll
+          for (int j = 0; j < 32; j += 2) {
+            const float p0 = ex2f(fmaf(s[j], c, -shc)), p1 = ex2f(fmaf(s[j + 1], c, -shc));
+            s4[(j >> 1) & 3] += p0 + p1;
+            pk[j >> 1] = pack_bf16(p0, p1);
+          }
+          tmem_st16(tmem + lane_off + (c0 >> 1), pk);
+        };
+        tmem_ld32_nowait(tmem + lane_off, bufa);
+        for (int c0 = 0; c0 < npad; c0 += 64) {
+          online_chunk(bufa, bufb, c0);
+          if (c0 + 32 < npad) online_chunk(bufb, bufa, c0 + 32);
+        }
+        m = sh;
+      } else {
       // Both passes keep the next 32-column TMEM load in flight while the current one is processed (two register
       // buffers) and use 4 independent max / sum chains.
-      float bufa[32], bufb[32];                                // named buffers: static register indexing
       // ---- pass 1: row max
       float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
       auto max_chunk = [&](float (&s)[32], float (&nxt)[32], int c0) {
@@ -782,7 +850,6 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       if (warp == 0) TRACE(1, 32);
       const float mc = (m == -INFINITY) ? 0.f : m * c;        // dead rows (qi >= L) only
       // ---- pass 2: p = exp2(s c - m c), row sum, packed bf16 P over the consumed S columns
-      float s4[4] = {0.f, 0.f, 0.f, 0.f};
       auto exp_chunk = [&](float (&s)[32], float (&nxt)[32], int c0) {
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
         // this chunk's P lands on columns [c0/2, c0/2+16), all below c0+32: it never touches S that is still unread
@@ -810,6 +877,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       for (int c0 = 0; c0 < npad; c0 += 64) {
         exp_chunk(bufa, bufb, c0);
         if (c0 + 32 < npad) exp_chunk(bufb, bufa, c0 + 32);
+      }
       }
       sum = (s4[0] + s4[1]) + (s4[2] + s4[3]);
       asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
@@ -848,6 +916,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(F_TM_COLS) : "memory");
   }
 }
+
 
 }  // namespace
 
@@ -902,16 +971,17 @@ int sc_attention_fwd_tc(const sc_attn_desc* a, cudaStream_t st) {
   if ((rc = sc_get_tensor_map(a->v, (uint64_t)a->H * HD, rows, a->v_rs, 64, ntile * TILE, &tv))) return rc;
   sc_count_kernel(SC_K_ATTN_FWD_TC, 1);
   const long total = (long)ntile * a->H * a->B;
+  static const int online = getenv("SC_ATT_FWD_TWO_PASS") ? 0 : 1; // A/B switch: exact row maximum first (reads S twice)
   const long slots = 2L * sc_num_sms();
   dim3 grid((unsigned)(total < slots ? total : slots));
   if (a->causal) {
     static sc_device_once once;
     if (once.first()) { SC_CUDA(cudaFuncSetAttribute(attn_fwd_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, F_SMEM_TOTAL)); once.done(); }
-    attn_fwd_tc_kernel<true><<<grid, F_THREADS, F_SMEM_TOTAL, st>>>(tq, tk, tv, *a);
+    attn_fwd_tc_kernel<true><<<grid, F_THREADS, F_SMEM_TOTAL, st>>>(tq, tk, tv, *a, online);
   } else {
     static sc_device_once once;
     if (once.first()) { SC_CUDA(cudaFuncSetAttribute(attn_fwd_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, F_SMEM_TOTAL)); once.done(); }
-    attn_fwd_tc_kernel<false><<<grid, F_THREADS, F_SMEM_TOTAL, st>>>(tq, tk, tv, *a);
+    attn_fwd_tc_kernel<false><<<grid, F_THREADS, F_SMEM_TOTAL, st>>>(tq, tk, tv, *a, online);
   }
   SC_LAUNCH_CHECK();
   return SC_OK;
