@@ -27,7 +27,8 @@ constexpr int OPER_BYTES = ROWS * 128;         // 32 KB
 constexpr int PT_BYTES = TILE * TILE * 2;      // 32 KB (two 64-wide k-blocks of 16 KB)
 constexpr int SM_Q = 0, SM_K = OPER_BYTES, SM_V = 2 * OPER_BYTES, SM_DO = 3 * OPER_BYTES;
 constexpr int SM_PT = 4 * OPER_BYTES, SM_DST = SM_PT + PT_BYTES;
-constexpr int SM_LSE = SM_DST + PT_BYTES;      // float[256] lse*log2e, float[256] delta
+constexpr int SM_EPI = SM_DST + PT_BYTES;      // 16 warps x 2 KB: 32 x 32 bf16 boxes (SWIZZLE_64B) of the dQ / dK / dV TMA stores
+constexpr int SM_LSE = SM_EPI + 16 * 2048;     // float[256] lse*log2e, float[256] delta
 constexpr int SM_BAR = SM_LSE + 2 * ROWS * 4;
 constexpr int SMEM_TOTAL = SM_BAR + 128;
 constexpr int NSOFT = 16;                      // softmax / epilogue warps: 4 per TMEM lane quarter x 32 columns
@@ -138,8 +139,9 @@ __device__ int g_trace_n[2];
 template <bool CAUSAL>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
-                   const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmdO, sc_attn_bwd_desc gd,
-                   const float* __restrict__ delta) {
+                   const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmdO,
+                   const __grid_constant__ CUtensorMap tmGQ, const __grid_constant__ CUtensorMap tmGK,
+                   const __grid_constant__ CUtensorMap tmGV, sc_attn_bwd_desc gd, const float* __restrict__ delta) {
   const sc_attn_desc& a = gd.fwd;
   extern __shared__ __align__(1024) uint8_t smem[];
   if ((smem_u32(smem) & 1023u) != 0u) __trap();
@@ -360,34 +362,67 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         dl[t] = qi < L ? delta[o] : 0.f;
       }
     };
+    // dV / dK / dQ leave through the TMA: 32 x 32 boxes per warp (lane quarter x one 32-column half of one tensor), packed
+    // to bf16, written once into a SWIZZLE_64B staging box and stored with cp.async.bulk.tensor over a 3-D map {H*64, L, B}
+    // whose second dimension clips the rows past the sample.  (The first version stored 32-byte pieces per lane: 32
+    // distinct lines per store instruction; the LSU wavefronts of all 16 warps cost ~2 k cycles per key tile and ~5 k at
+    // item ends -- on the softmax warps' critical path, SC_ATT_TRACE.)
+    const uint32_t estage = sbase + SM_EPI + warp * 2048;
+    // (16 columns at a time: the kernel runs at its 96-register cap -- 18 warps, five per SM sub-partition)
+    auto stage_and_store = [&](const CUtensorMap* map, uint32_t tcol, bool live, float scale, int col0, int row0, int b) {
+      bulk_wait_read<0>();                               // (elected lane) the previous store has read the staging box
+      __syncwarp();
+      const int sw = (lane >> 1) & 3;
+      if (live) {
+#pragma unroll 1
+        for (int hf = 0; hf < 2; ++hf) {
+          float v[16];
+          tmem_ld16(tmem + lane_off + tcol + hf * 16, v);
+#pragma unroll
+          for (int j = 0; j < 2; ++j)
+            sts128u(estage + lane * 64 + (((hf * 2 + j) ^ sw) << 4), pack_bf16(v[8 * j] * scale, v[8 * j + 1] * scale),
+                    pack_bf16(v[8 * j + 2] * scale, v[8 * j + 3] * scale), pack_bf16(v[8 * j + 4] * scale, v[8 * j + 5] * scale),
+                    pack_bf16(v[8 * j + 6] * scale, v[8 * j + 7] * scale));
+        }
+      }
+      return live;
+    };
+    auto release_and_store = [&](const CUtensorMap* map, bool live, int col0, int row0, int b) {
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      __syncwarp();
+      if (live) {                                         // warp-uniform; rows past L inside the box are clipped by the map
+        asm volatile(
+            "{\n\t.reg .pred e;\n\t"
+            "elect.sync _|e, 0xffffffff;\n\t"
+            "@e cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];\n\t}"
+            ::"l"((uint64_t)map), "r"(estage), "r"(col0), "r"(row0), "r"(b) : "memory");
+      }
+      bulk_commit();
+    };
     auto dkv_epilogue = [&](int kt, int h, int b) {
-      // dV / dK of a key tile (TMEM lanes = keys); this warp handles 16 of the 64 head-dim columns
+      // dV / dK of a key tile (TMEM lanes = keys): column groups 0,1 take the halves of dV, 2,3 those of dK
       mbar_wait(bar_dkv, ph_dkv);
       ph_dkv ^= 1;
       tcgen05_fence_after();
-      float v[16], kk[16];
-      tmem_ld16(tmem + lane_off + TM_DV + cg * 16, v);
-      tmem_ld16(tmem + lane_off + TM_DK + cg * 16, kk);
+      const int row0 = kt * TILE + quarter * 32;
+      const CUtensorMap* map = cg < 2 ? &tmGV : &tmGK;
+      stage_and_store(map, (cg < 2 ? TM_DV : TM_DK) + (cg & 1) * 32, row0 < L, cg < 2 ? 1.0f : a.scale, 0, 0, 0);
       tcgen05_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_dkv_free);
-      const int key = kt * TILE + r;
-      if (key < L) {
-        store16_bf16((bf16*)gd.d_v + (long)b * a.v_bs + (long)key * a.v_rs + h * HD + cg * 16, v, 1.0f);
-        store16_bf16((bf16*)gd.d_k + (long)b * a.k_bs + (long)key * a.k_rs + h * HD + cg * 16, kk, a.scale);
-      }
+      release_and_store(map, row0 < L, h * HD + (cg & 1) * 32, row0, b);
     };
     auto dq_epilogue = [&](int h, int b) {
-      // dQ (TMEM lanes = queries): bar_dkv of the item's last key tile was committed after every MMA of the item
-      float v0[16], v1[16];
-      tmem_ld16(tmem + lane_off + TM_DQ + cg * 16, v0);
-      if (ntile > 1) tmem_ld16(tmem + lane_off + TM_DQ + 64 + cg * 16, v1);
+      // dQ (TMEM lanes = queries): bar_dkv of the item's last key tile was committed after every MMA of the item;
+      // column groups 0,1 take the halves of query tile 0, groups 2,3 those of query tile 1
+      const int qt = cg >> 1;
+      const int row0 = qt * TILE + quarter * 32;
+      const bool live = qt < ntile && row0 < L;
+      stage_and_store(&tmGQ, TM_DQ + qt * 64 + (cg & 1) * 32, live, a.scale, 0, 0, 0);
       tcgen05_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_dq_free);
-      if (r < L) store16_bf16((bf16*)gd.d_q + (long)b * a.q_bs + (long)r * a.q_rs + h * HD + cg * 16, v0, a.scale);
-      if (ntile > 1 && TILE + r < L)
-        store16_bf16((bf16*)gd.d_q + (long)b * a.q_bs + (long)(TILE + r) * a.q_rs + h * HD + cg * 16, v1, a.scale);
+      release_and_store(&tmGQ, live, h * HD + (cg & 1) * 32, row0, b);
     };
     // The read-out of an item's last dV / dK and of its dQ is deferred until this warp has delivered the first tile of
     // the NEXT item, so the MMA pipe never waits for the drain (the control warp holds the next item's accumulating
@@ -481,6 +516,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       dkv_epilogue(ntile - 1, prev_h, prev_b);
       dq_epilogue(prev_h, prev_b);
     }
+    bulk_wait_all();                                       // staging smem must outlive the last TMA stores
   }
   tcgen05_fence_before();
   __syncthreads();
@@ -519,7 +555,8 @@ constexpr int F_NSOFT = SC_ATT_FWD_SOFT_WARPS;          // 4 or 8
 constexpr int F_SM_BAR = F_SM_V + OPER_BYTES;
 constexpr int F_SM_X = F_SM_BAR + 64;                   // float [2 (max | sum)][2 (half)][128 rows]
 constexpr int F_SM_P = F_SM_X + 2 * 2 * 128 * 4;        // parked P of the upper half: [3 chunks][128 rows][64 B], XOR-swizzled
-constexpr int F_SMEM_TOTAL = F_SM_P + (F_NSOFT == 8 ? 3 * 128 * 64 : 0);
+constexpr int F_SM_O = ((F_SM_P + (F_NSOFT == 8 ? 3 * 128 * 64 : 0)) + 1023) / 1024 * 1024;   // 4 x 4 KB: O boxes of the TMA stores (SWIZZLE_128B)
+constexpr int F_SMEM_TOTAL = F_SM_O + 4 * 4096;
 constexpr int F_THREADS = (F_NSOFT + 1) * 32;
 constexpr uint32_t F_TM_O = 128, F_TM_COLS = 256;
 
@@ -534,7 +571,7 @@ SC_DEVINL void tmem_st16(uint32_t taddr, const uint32_t* r) {
 template <bool CAUSAL>
 __global__ void __launch_bounds__(F_THREADS, 2)
 attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
-                   const __grid_constant__ CUtensorMap tmV, sc_attn_desc a, int online) {
+                   const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmO, sc_attn_desc a, int online) {
   extern __shared__ __align__(1024) uint8_t smem[];
   if ((smem_u32(smem) & 1023u) != 0u) __trap();
   const uint32_t sbase = smem_u32(smem);
@@ -899,15 +936,31 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     __syncwarp();
     if (lane == 0) mbar_arrive(bar_free);
     if (warp == 0) TRACE(1, 35);
-    if (warp_live && qi < L) {
+    if (warp_live) {
+      // O leaves through the TMA (32 x 64 box per warp over a 3-D map {H*64, L, B}: rows past L are clipped): per-lane
+      // 128-byte row stores cost 32 LSU wavefronts per instruction, ~2.4 k cycles per item (SC_ATT_TRACE)
       const float inv = 1.0f / sum;
-      bf16* dst = (bf16*)a.o + (long)b * a.o_bs + (long)qi * a.o_rs + h * HD;
+      const uint32_t ostage = sbase + F_SM_O + warp * 4096;
+      bulk_wait_read<0>();
+      __syncwarp();
 #pragma unroll
-      for (int j = 0; j < 4; ++j) store16_bf16(dst + 16 * j, o + 16 * j, inv);
-      a.lse[((long)b * a.H + h) * L + qi] = m * a.scale + logf(sum);
+      for (int j = 0; j < 8; ++j)
+        sts128u(ostage + lane * 128 + ((j ^ (lane & 7)) << 4), pack_bf16(o[8 * j] * inv, o[8 * j + 1] * inv),
+                pack_bf16(o[8 * j + 2] * inv, o[8 * j + 3] * inv), pack_bf16(o[8 * j + 4] * inv, o[8 * j + 5] * inv),
+                pack_bf16(o[8 * j + 6] * inv, o[8 * j + 7] * inv));
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      __syncwarp();
+      asm volatile(
+          "{\n\t.reg .pred e;\n\t"
+          "elect.sync _|e, 0xffffffff;\n\t"
+          "@e cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];\n\t}"
+          ::"l"((uint64_t)&tmO), "r"(ostage), "r"(h * HD), "r"(qt * TILE + warp * 32), "r"(b) : "memory");
+      bulk_commit();
+      if (qi < L) a.lse[((long)b * a.H + h) * L + qi] = m * a.scale + logf(sum);
     }
     if (warp == 0) TRACE(1, 36);
     }   // item loop
+    if constexpr (F_NSOFT == 4) bulk_wait_all();           // staging smem must outlive the last TMA stores
   }
   tcgen05_fence_before();
   __syncthreads();
@@ -942,6 +995,11 @@ int sc_attention_bwd_tc(const sc_attn_bwd_desc* g, float* delta, cudaStream_t st
   if ((rc = sc_get_tensor_map(a->k, (uint64_t)a->H * HD, rows, a->k_rs, 64, TILE, &tk))) return rc;
   if ((rc = sc_get_tensor_map(a->v, (uint64_t)a->H * HD, rows, a->v_rs, 64, TILE, &tv))) return rc;
   if ((rc = sc_get_tensor_map(g->d_o, (uint64_t)a->H * HD, rows, a->o_rs, 64, TILE, &tdo))) return rc;
+  // gradient outputs: 3-D {H*64, L, B}, 32 x 32 boxes, rows past L clipped
+  CUtensorMap gq, gk, gv;
+  if ((rc = sc_get_tensor_map_3d(g->d_q, (uint64_t)a->H * HD, L, a->B, a->q_rs, a->q_bs, 32, 32, 64, &gq))) return rc;
+  if ((rc = sc_get_tensor_map_3d(g->d_k, (uint64_t)a->H * HD, L, a->B, a->k_rs, a->k_bs, 32, 32, 64, &gk))) return rc;
+  if ((rc = sc_get_tensor_map_3d(g->d_v, (uint64_t)a->H * HD, L, a->B, a->v_rs, a->v_bs, 32, 32, 64, &gv))) return rc;
   sc_count_kernel(SC_K_ATTN_BWD_TC, 2);
   const long n = rows * a->H;
   attn_delta_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>((const bf16*)a->o, (const bf16*)g->d_o, a->o_bs, a->o_rs, a->B,
@@ -951,11 +1009,11 @@ int sc_attention_bwd_tc(const sc_attn_bwd_desc* g, float* delta, cudaStream_t st
   if (a->causal) {
     static sc_device_once once;
     if (once.first()) { SC_CUDA(cudaFuncSetAttribute(attn_bwd_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL)); once.done(); }
-    attn_bwd_tc_kernel<true><<<grid, TC_THREADS, SMEM_TOTAL, st>>>(tq, tk, tv, tdo, *g, delta);
+    attn_bwd_tc_kernel<true><<<grid, TC_THREADS, SMEM_TOTAL, st>>>(tq, tk, tv, tdo, gq, gk, gv, *g, delta);
   } else {
     static sc_device_once once;
     if (once.first()) { SC_CUDA(cudaFuncSetAttribute(attn_bwd_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL)); once.done(); }
-    attn_bwd_tc_kernel<false><<<grid, TC_THREADS, SMEM_TOTAL, st>>>(tq, tk, tv, tdo, *g, delta);
+    attn_bwd_tc_kernel<false><<<grid, TC_THREADS, SMEM_TOTAL, st>>>(tq, tk, tv, tdo, gq, gk, gv, *g, delta);
   }
   SC_LAUNCH_CHECK();
   return SC_OK;
@@ -969,6 +1027,8 @@ int sc_attention_fwd_tc(const sc_attn_desc* a, cudaStream_t st) {
   if ((rc = sc_get_tensor_map(a->q, (uint64_t)a->H * HD, rows, a->q_rs, 64, TILE, &tq))) return rc;
   if ((rc = sc_get_tensor_map(a->k, (uint64_t)a->H * HD, rows, a->k_rs, 64, ntile * TILE, &tk))) return rc;
   if ((rc = sc_get_tensor_map(a->v, (uint64_t)a->H * HD, rows, a->v_rs, 64, ntile * TILE, &tv))) return rc;
+  CUtensorMap to;
+  if ((rc = sc_get_tensor_map_3d(a->o, (uint64_t)a->H * HD, L, a->B, a->o_rs, a->o_bs, 64, 32, 128, &to))) return rc;
   sc_count_kernel(SC_K_ATTN_FWD_TC, 1);
   const long total = (long)ntile * a->H * a->B;
   static const int online = getenv("SC_ATT_FWD_TWO_PASS") ? 0 : 1; // A/B switch: exact row maximum first (reads S twice)
@@ -977,11 +1037,11 @@ int sc_attention_fwd_tc(const sc_attn_desc* a, cudaStream_t st) {
   if (a->causal) {
     static sc_device_once once;
     if (once.first()) { SC_CUDA(cudaFuncSetAttribute(attn_fwd_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, F_SMEM_TOTAL)); once.done(); }
-    attn_fwd_tc_kernel<true><<<grid, F_THREADS, F_SMEM_TOTAL, st>>>(tq, tk, tv, *a, online);
+    attn_fwd_tc_kernel<true><<<grid, F_THREADS, F_SMEM_TOTAL, st>>>(tq, tk, tv, to, *a, online);
   } else {
     static sc_device_once once;
     if (once.first()) { SC_CUDA(cudaFuncSetAttribute(attn_fwd_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, F_SMEM_TOTAL)); once.done(); }
-    attn_fwd_tc_kernel<false><<<grid, F_THREADS, F_SMEM_TOTAL, st>>>(tq, tk, tv, *a, online);
+    attn_fwd_tc_kernel<false><<<grid, F_THREADS, F_SMEM_TOTAL, st>>>(tq, tk, tv, to, *a, online);
   }
   SC_LAUNCH_CHECK();
   return SC_OK;

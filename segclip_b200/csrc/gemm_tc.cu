@@ -110,6 +110,46 @@ int sc_get_tensor_map_any(const void* ptr, uint64_t dim0, uint64_t dim1, uint64_
   return SC_OK;
 }
 
+// bf16 3-D tensor map {dim0 (contiguous), dim1, dim2} with element strides for dims 1 and 2, box {box0, box1, 1}: the
+// attention backward stores dQ / dK / dV tiles through it so that rows past a sample's L are clipped by the TMA itself.
+int sc_get_tensor_map_3d(const void* ptr, uint64_t dim0, uint64_t dim1, uint64_t dim2, uint64_t stride1_elems,
+                         uint64_t stride2_elems, uint32_t box0, uint32_t box1, int swizzle_bytes, CUtensorMap* out) {
+  static std::mutex mu;
+  static std::unordered_map<MapKey, CUtensorMap, MapKeyHash> cache;
+  MapKey key{ptr, dim0, dim1 | (dim2 << 32), stride1_elems | (stride2_elems << 32), box0, box1, swizzle_bytes | (3 << 24)};
+  {
+    std::lock_guard<std::mutex> g(mu);
+    auto it = cache.find(key);
+    if (it != cache.end()) {
+      *out = it->second;
+      return SC_OK;
+    }
+  }
+  EncodeTiledFn enc = get_encode_fn();
+  if (!enc) {
+    sc_set_error("cuTensorMapEncodeTiled not available from the CUDA driver");
+    return SC_ERR_CUDA;
+  }
+  cuuint64_t gdim[3] = {dim0, dim1, dim2};
+  cuuint64_t gstride[2] = {stride1_elems * 2, stride2_elems * 2};
+  cuuint32_t box[3] = {box0, box1, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(ptr), gdim, gstride, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : (swizzle_bytes == 32 ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_128B),
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    sc_set_error("cuTensorMapEncodeTiled(3d) failed (%d): ptr=%p dims=(%llu,%llu,%llu) strides=(%llu,%llu) box=(%u,%u)", (int)r, ptr,
+                 (unsigned long long)dim0, (unsigned long long)dim1, (unsigned long long)dim2, (unsigned long long)stride1_elems,
+                 (unsigned long long)stride2_elems, box0, box1);
+    return SC_ERR_CUDA;
+  }
+  std::lock_guard<std::mutex> g(mu);
+  if (cache.size() > 65536) cache.clear();
+  cache[key] = *out;
+  return SC_OK;
+}
+
 
 // Picks the compile-time specialised epilogue (tc::EF_*) for a descriptor, or EF_GENERIC.
 int sc_select_epilogue(const sc_gemm_desc* d, int splits) {

@@ -628,4 +628,6 @@ int sc_get_tensor_map_sw(const void* ptr, uint64_t dim0, uint64_t dim1, uint64_t
                          int swizzle_bytes, CUtensorMap* out);
 int sc_get_tensor_map_any(const void* ptr, uint64_t dim0, uint64_t dim1, uint64_t stride_elems, uint32_t box0, uint32_t box1,
                           int swizzle_bytes, int elem_bytes, CUtensorMap* out);
+int sc_get_tensor_map_3d(const void* ptr, uint64_t dim0, uint64_t dim1, uint64_t dim2, uint64_t stride1_elems,
+                         uint64_t stride2_elems, uint32_t box0, uint32_t box1, int swizzle_bytes, CUtensorMap* out);
 int sc_select_epilogue(const sc_gemm_desc* d, int splits);
