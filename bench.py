@@ -271,7 +271,7 @@ def main():
         "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
         "data": "synthetic",
         "config": {"workload": workload_name(args), "per_gpu_batch": B, "global_batch": B * world,
-                   "parallelism": "dp%d" % world, "grad_sync": ("ddp" if args.ddp else "native-overlapped") if world > 1 else "none", "l2": "per-step working set (GBs of activations) exceeds the 126 MB L2"},
+                   "parallelism": "dp%d" % world, "grad_sync": ("ddp" if args.ddp else ("native-overlapped, NVLS multimem kernel" if model._engine.nvls is not None else "native-overlapped, NCCL buckets")) if world > 1 else "none", "l2": "per-step working set (GBs of activations) exceeds the 126 MB L2"},
         "e2e": {"value": B * world / (ms_e2e / 1e3), "unit": "pairs/s",
                 "h2d_bytes_per_step": int(host["input_ids"].numel() * 8 + host["image"].numel() * 4 +
                                           (host["image_seg"].numel() * 8 if args.heads else 0)),
@@ -298,7 +298,9 @@ def main():
 def gemm_traffic(args):
     """Average DRAM bytes (read + write) per gemm_tc2_kernel launch of this workload, from the committed ncu pass
     (profiles/r1_gemm_traffic.json, written by tools/summarize_launches.py --traffic); None for other workloads."""
-    path = os.path.join(ROOT, "profiles", "r1_gemm_traffic.json")
+    path = os.path.join(ROOT, "profiles", "r2_gemm_traffic.json")
+    if not os.path.exists(path):
+        path = os.path.join(ROOT, "profiles", "r1_gemm_traffic.json")
     if args.model != "vitb16" or args.heads or args.batch != 256 or not os.path.exists(path):
         return None
     return json.load(open(path)).get("dram_bytes_per_launch")

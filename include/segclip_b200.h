@@ -226,11 +226,16 @@ int sc_blockdiag_expand(const float* w, void* dense, int C, int groups, int dtyp
 int sc_blockdiag_reduce(const float* dense_grad, float* dw, int C, int groups, void* stream);
 
 /* Non-overlapping patch extraction for conv1 (kernel == stride, module_clip_vtransformer.py:21,56):
- * out[r*ld + c*p*p + y*p + x] = image[r / rows_per_img, c, (pid / grid)*p + y, (pid % grid)*p + x],
- * pid = patch_idx ? patch_idx[r] : r % rows_per_img (MAE pass: only kept patches are embedded).
+ * out[r*ld + c*p*p + y*p + x] = image[r / rows_per_img, c, (pid / grid_w)*p + y, (pid % grid_w)*p + x],
+ * pid = patch_idx ? patch_idx[r] : r % rows_per_img (MAE pass: only kept patches are embedded); the image is
+ * [*, 3, grid_h*p, grid_w*p] (training: square; inference also takes the 2x / rectangular sizes of the reference).
  * ld >= 3*p*p is the row pitch of `out` (padded to a multiple of 8 for TMA when 3*p*p is not, e.g. patch 14). */
 int sc_im2col(const float* image, void* out, int out_dtype, int64_t ld, const int32_t* patch_idx, int64_t rows,
-              int rows_per_img, int grid, int patch, void* stream);
+              int rows_per_img, int grid_h, int grid_w, int patch, void* stream);
+/* Inference at another input size: bicubic (A = -0.75, align_corners = False) interpolation of the patch part of the
+ * positional table [src_h, src_w, D] -> [dst_h, dst_w, D], fp32 (VisualTransformer.get_pos_embed,
+ * modules/module_clip_vtransformer.py:35-53; same arithmetic as F.interpolate(mode='bicubic')). */
+int sc_bicubic_resize(const float* src, float* dst, int src_h, int src_w, int dst_h, int dst_w, int D, void* stream);
 
 /* "Next" row: uint8 image boundary.  out = (img/255 - mean[c]) / std[c] for a [*, 3, H, W] uint8
  * batch already on the device (hw = H*W; mean3/std3 are HOST arrays of 3 floats): the normalisation of

@@ -335,13 +335,27 @@ def random_masking_keep_cls(x, u2, mask_ratio=0.75):
     return xm, mask, ids_restore, ids_keep
 
 
-def patch_embed(image, p, cfg):
-    """VisualTransformer.forward up to ln_pre, modules/module_clip_vtransformer.py:55-65."""
+def eval_pos_embed(pos, h_, w_):
+    """VisualTransformer.get_pos_embed in eval mode (modules/module_clip_vtransformer.py:35-53): the patch part of the table
+    is bicubically interpolated (align_corners=False) to the h_ x w_ grid of the input; the CLS row is kept."""
+    pos_cls, pos_patch = pos[:1], pos[1:]
+    n, dim = pos_patch.shape
+    if h_ * w_ == n and h_ == w_:
+        return pos
+    g = int(math.sqrt(n))
+    r = F.interpolate(pos_patch.reshape(1, g, g, dim).permute(0, 3, 1, 2), size=(h_, w_), mode="bicubic", align_corners=False)
+    return torch.cat([pos_cls, r.permute(0, 2, 3, 1).reshape(-1, dim)], dim=0)
+
+
+def patch_embed(image, p, cfg, training=True):
+    """VisualTransformer.forward up to ln_pre, modules/module_clip_vtransformer.py:55-65 (training: the raw table, :36-37)."""
     v = "clip.visual."
     x = F.conv2d(image, p[v + "conv1.weight"], stride=cfg["patch"])
+    h_, w_ = x.shape[-2:]
     x = x.flatten(2).transpose(1, 2)
     cls = p[v + "class_embedding"].expand(x.shape[0], 1, -1)
-    x = torch.cat([cls, x], dim=1) + p[v + "positional_embedding"]
+    pos = p[v + "positional_embedding"] if training else eval_pos_embed(p[v + "positional_embedding"], h_, w_)
+    x = torch.cat([cls, x], dim=1) + pos
     return ln(x, p, v + "ln_pre")
 
 
@@ -351,7 +365,7 @@ def encode_image(image, p, cfg, u1, kv_layout, forced_idx=None, training=True, f
     per-channel arg-max of the centre max-pooling (reduced-precision comparisons only)."""
     v, t = "clip.visual.", "clip.visual.transformer."
     heads = cfg["vision_width"] // 64
-    x = patch_embed(image, p, cfg)[:, 1:]                      # CLS dropped (:419)
+    x = patch_embed(image, p, cfg, training)[:, 1:]            # CLS dropped (:419)
     for i in range(cfg["first_stage_layer"]):
         x = self_attn_block(x, p, f"{t}layers0.{i}.", heads)
     sx, hard, soft, _, idx = semantic_learner(x, p, t + "semantic_layer2.", heads, u1, kv_layout, forced_idx, training)

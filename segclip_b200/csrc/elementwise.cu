@@ -132,15 +132,45 @@ __global__ void blockdiag_reduce_kernel(const float* __restrict__ dense, float* 
 // ---------------------------------------------------------------- patch extraction (im2col for stride == kernel)
 template <typename T>
 __global__ void im2col_kernel(const float* __restrict__ img, T* __restrict__ out, long ld, const int* __restrict__ patch_idx,
-                              int rows_per_img, int grid, int p, int res) {
+                              int rows_per_img, int grid_w, int p, int res_h, int res_w) {
   const long row = blockIdx.x;
   const int b = row / rows_per_img;
   const int pid = patch_idx ? patch_idx[row] : (int)(row % rows_per_img);
-  const int py0 = (pid / grid) * p, px0 = (pid % grid) * p;
+  const int py0 = (pid / grid_w) * p, px0 = (pid % grid_w) * p;
   const int K = 3 * p * p;
   for (int k = threadIdx.x; k < K; k += blockDim.x) {
     int c = k / (p * p), r = (k / p) % p, q = k % p;
-    out[row * ld + k] = from_f32<T>(img[(((long)b * 3 + c) * res + py0 + r) * res + px0 + q]);
+    out[row * ld + k] = from_f32<T>(img[(((long)b * 3 + c) * res_h + py0 + r) * res_w + px0 + q]);
+  }
+}
+
+// ---------------------------------------------------------------- bicubic resize of the positional table (inference)
+// VisualTransformer.get_pos_embed (modules/module_clip_vtransformer.py:35-53): F.interpolate(mode='bicubic',
+// align_corners=False) of the [g, g, D] patch table to [h, w, D].  Same arithmetic as ATen's upsample_bicubic2d: source
+// coordinate scale * (dst + 0.5) - 0.5 (not clamped), cubic convolution with A = -0.75, taps clamped to the border.
+SC_DEVINL float cubic1(float x) { return ((-0.75f + 2.f) * x - (-0.75f + 3.f)) * x * x + 1.f; }
+SC_DEVINL float cubic2(float x) { return ((-0.75f * x - 5.f * -0.75f) * x + 8.f * -0.75f) * x - 4.f * -0.75f; }
+__global__ void bicubic_resize_kernel(const float* __restrict__ src, float* __restrict__ dst, int gh, int gw, int h, int w, int D) {
+  const int oy = blockIdx.x / w, ox = blockIdx.x % w;
+  const float sy = (float)gh / h * (oy + 0.5f) - 0.5f, sx = (float)gw / w * (ox + 0.5f) - 0.5f;
+  const int iy = (int)floorf(sy), ix = (int)floorf(sx);
+  const float ty = sy - iy, tx = sx - ix;
+  const float wy[4] = {cubic2(ty + 1.f), cubic1(ty), cubic1(1.f - ty), cubic2(2.f - ty)};
+  const float wx[4] = {cubic2(tx + 1.f), cubic1(tx), cubic1(1.f - tx), cubic2(2.f - tx)};
+  for (int d = threadIdx.x; d < D; d += blockDim.x) {
+    float acc = 0.f;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int y = min(max(iy - 1 + i, 0), gh - 1);
+      float rowv = 0.f;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int x = min(max(ix - 1 + j, 0), gw - 1);
+        rowv += wx[j] * src[((long)y * gw + x) * D + d];
+      }
+      acc += wy[i] * rowv;
+    }
+    dst[((long)oy * w + ox) * D + d] = acc;
   }
 }
 
@@ -337,13 +367,23 @@ int sc_blockdiag_reduce(const float* dense_grad, float* dw, int C, int groups, v
 }
 
 int sc_im2col(const float* image, void* out, int out_dtype, int64_t ld, const int32_t* patch_idx, int64_t rows,
-              int rows_per_img, int grid, int patch, void* stream) {
-  SC_CHECK_ARG(image && out && rows > 0 && ld >= 3 * patch * patch, "sc_im2col: bad args");
+              int rows_per_img, int grid_h, int grid_w, int patch, void* stream) {
+  SC_CHECK_ARG(image && out && rows > 0 && ld >= 3 * patch * patch && grid_h > 0 && grid_w > 0, "sc_im2col: bad args");
   sc_count_launch(1);
   if (out_dtype == SC_F32)
-    im2col_kernel<float><<<(unsigned)rows, 256, 0, (cudaStream_t)stream>>>(image, (float*)out, ld, patch_idx, rows_per_img, grid, patch, grid * patch);
+    im2col_kernel<float><<<(unsigned)rows, 256, 0, (cudaStream_t)stream>>>(image, (float*)out, ld, patch_idx, rows_per_img, grid_w, patch,
+                                                                          grid_h * patch, grid_w * patch);
   else
-    im2col_kernel<bf16><<<(unsigned)rows, 256, 0, (cudaStream_t)stream>>>(image, (bf16*)out, ld, patch_idx, rows_per_img, grid, patch, grid * patch);
+    im2col_kernel<bf16><<<(unsigned)rows, 256, 0, (cudaStream_t)stream>>>(image, (bf16*)out, ld, patch_idx, rows_per_img, grid_w, patch,
+                                                                         grid_h * patch, grid_w * patch);
+  SC_LAUNCH_CHECK();
+  return SC_OK;
+}
+
+int sc_bicubic_resize(const float* src, float* dst, int src_h, int src_w, int dst_h, int dst_w, int D, void* stream) {
+  SC_CHECK_ARG(src && dst && src_h > 0 && src_w > 0 && dst_h > 0 && dst_w > 0 && D > 0, "sc_bicubic_resize: bad args");
+  sc_count_launch(1);
+  bicubic_resize_kernel<<<dst_h * dst_w, 256, 0, (cudaStream_t)stream>>>(src, dst, src_h, src_w, dst_h, dst_w, D);
   SC_LAUNCH_CHECK();
   return SC_OK;
 }

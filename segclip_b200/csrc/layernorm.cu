@@ -597,7 +597,8 @@ extern "C" int sc_layernorm_bwd(const sc_ln_bwd_desc* d, void* stream) {
                     ((uintptr_t)d->dx & 15) == 0 && ((uintptr_t)d->gamma & 15) == 0;
   // the prefetch ring pays off on long rows and many of them (measured: D = 768 x 50176 rows 5.0 vs 4.0 TB/s; D = 512 x 19712
   // rows 3.7 vs 4.6 TB/s: too few rows per warp to amortise the prologue / final reduction)
-  if (!old_kernel && !reg_kernel && vec8 && d->D >= 640 && d->rows >= 16384) {
+  static const int tma_min_d = [] { const char* e = getenv("SC_LN_TMA_MIN_D"); return e ? atoi(e) : 640; }();
+  if (!old_kernel && !reg_kernel && vec8 && d->D >= tma_min_d && d->rows >= 16384) {
     int rc = SC_ERR_UNSUPPORTED;
     switch (key) {
       case 0: rc = launch_bwd_tma<float, float, float>(*d, st); break;

@@ -86,6 +86,8 @@ class Engine:
         c = self.cfg
         self.vw, self.tw, self.E = c["vision_width"], c["text_width"], c["embed_dim"]
         self.patch, self.grid = c["patch"], c["grid"]
+        self.grid_hw = (self.grid, self.grid)        # token grid of the input (inference clones may differ, see for_grid)
+        self.pos_table = None                        # resized positional table of an inference clone
         self.Lp = self.grid ** 2
         self.Tctx = c["context"]
         self.Hv, self.Ht = self.vw // 64, self.tw // 64
@@ -163,6 +165,31 @@ class Engine:
         self.goffs = dict(zip(names, offs))
         self.gsizes = dict(zip(names, sizes))
         self.grads = {n: self.gflat[o:o + s].view(self.params[n].shape) for n, o, s in zip(names, offs, sizes)}
+
+    # ------------------------------------------------------------------ inference at another input size
+    def for_grid(self, gh, gw):
+        """Inference-only view of this engine for inputs of gh x gw patches (module_clip_vtransformer.py:35-53): shares every
+        parameter / shadow / gradient buffer, owns its plans and a bicubically resized positional table.  The reference's
+        SegViT takes its semantic branch only for n or 4 n tokens (module_seg_vit.py:423); the same rule is enforced."""
+        key = (gh, gw)
+        clones = self.__dict__.setdefault("_grid_clones", {})
+        if key not in clones:
+            n = self.grid * self.grid
+            if gh * gw not in (n, 4 * n):
+                raise L.SegclipB200Error("inference input of %d x %d patches: the reference's SegViT supports %d or %d patch tokens only "
+                                         "(modules/module_seg_vit.py:423)" % (gh, gw, n, 4 * n))
+            import copy
+            c = copy.copy(self)
+            c.grid_hw, c.Lp = key, gh * gw
+            c.plans, c.eval_plans = {}, {}
+            c.use_mae = c.use_kl = False
+            c.gather, c.sync_group, c.nvls = None, None, None
+            c.world, c.rank = 1, 0
+            c.pos_table = torch.empty(gh * gw, self.vw, device=self.dev)
+            c.pos_op = ops.bicubic_resize_op(self.P("clip.visual.positional_embedding")[1:], c.pos_table, (self.grid, self.grid), key)
+            c.prep_ops = list(self.prep_ops) + [c.pos_op]          # recomputed per call: follows parameter updates
+            clones[key] = c
+        return clones[key]
 
     # ------------------------------------------------------------------ native gradient all-reduce
     def enable_grad_sync(self, group, bucket_mb=None):
@@ -256,7 +283,7 @@ class Engine:
         dev, T = self.dev, self.T
         f32, i32 = torch.float32, torch.int32
         is_bf16 = T != f32
-        res = self.patch * self.grid
+        res_h, res_w = self.patch * self.grid_hw[0], self.patch * self.grid_hw[1]
 
         def buf(name, shape, dtype=f32, zero=False):
             assert name not in pl.bufs, name
@@ -283,7 +310,7 @@ class Engine:
 
         # ---------------- inputs
         ids = buf("in.ids", (B, self.Tctx), torch.int64)
-        image = buf("in.image", (B, 3, res, res))
+        image = buf("in.image", (B, 3, res_h, res_w))
         seg = buf("in.seg", (B, self.Lp), torch.int64)
         u1 = buf("in.u1", (B, G, self.Lp))
         u2 = buf("in.u2", (B, self.Lp + 1))
@@ -504,9 +531,9 @@ class Engine:
             cols = buf(tag + ".cols", (M, Kp), T, zero=(Kp != K))
             if Kp != K:
                 pl.zero[:] = [z for z in pl.zero if z is not cols]      # padding zeroed once; im2col never touches it
-            pl.f(ops.im2col_op(image, cols, patch_idx, rows_per_img, self.grid, self.patch))
+            pl.f(ops.im2col_op(image, cols, patch_idx, rows_per_img, self.grid_hw, self.patch))
             pre = buf(tag + ".pre", (M, self.vw))
-            pos = self.P(v + "positional_embedding")[1:]
+            pos = self.P(v + "positional_embedding")[1:] if self.pos_table is None else self.pos_table
             pl.f(ops.gemm_op(cols, self.conv_weight(), pre, rowbias=pos, rowbias_idx=patch_idx, rowbias_mod=self.Lp))
             x0 = buf(tag + ".x0", (M, self.vw))
             pl.f(ops.layernorm_op(pre, self.P(v + "ln_pre.weight"), self.P(v + "ln_pre.bias"), x0))

@@ -198,9 +198,13 @@ class _ClipFacade(_Node):
         eng = owner._get_engine()
         image = torch.as_tensor(image)
         B = image.shape[0]
-        if image.shape[-1] != eng.patch * eng.grid:
-            raise NotImplementedError("bicubic positional-embedding resize (module_clip_vtransformer.py:35-53) is not built: "
-                                      "inputs must be %dx%d" % (eng.patch * eng.grid, eng.patch * eng.grid))
+        gh, gw = image.shape[-2] // eng.patch, image.shape[-1] // eng.patch
+        if image.shape[-2] != gh * eng.patch or image.shape[-1] != gw * eng.patch:
+            raise ValueError("image size %s is not a multiple of the patch size %d" % (tuple(image.shape[-2:]), eng.patch))
+        if (gh, gw) != (eng.grid, eng.grid):
+            # another input size (zero-shot segmentation at 2x the training resolution, vit_seg.py:157): inference clone of the
+            # engine with a bicubically resized positional table (module_clip_vtransformer.py:35-53)
+            eng = eng.for_grid(gh, gw)
         b = eng.infer(B, image=image.to(eng.dev), norm=owner.image_norm)
         hidden = b["v.hidden9"].view(B, G + 1, eng.E).clone()
         x = hidden[:, 0]

@@ -196,9 +196,17 @@ def blockdiag_reduce_op(dense_grad, dw, groups):
     return Op("sc_blockdiag_reduce", (dense_grad.data_ptr(), dw.data_ptr(), Cc, groups), (dense_grad, dw))
 
 
-def im2col_op(image, out, patch_idx, rows_per_img, grid, patch):
+def im2col_op(image, out, patch_idx, rows_per_img, grid_hw, patch):
+    gh, gw = grid_hw
     return Op("sc_im2col", (image.data_ptr(), out.data_ptr(), L.dt(out), out.stride(0), _p(patch_idx), out.shape[0],
-                            rows_per_img, grid, patch), (image, out, patch_idx))
+                            rows_per_img, gh, gw, patch), (image, out, patch_idx))
+
+
+def bicubic_resize_op(src, dst, src_hw, dst_hw):
+    """[sh*sw, D] -> [dh*dw, D] fp32 (positional table, inference at another input size)."""
+    assert src.dtype == dst.dtype == torch.float32 and src.is_contiguous() and dst.is_contiguous()
+    return Op("sc_bicubic_resize", (src.data_ptr(), dst.data_ptr(), src_hw[0], src_hw[1], dst_hw[0], dst_hw[1], src.shape[-1]),
+              (src, dst))
 
 
 def text_embed_op(ids, tok, pos, out, eot_rows, B, T, W):

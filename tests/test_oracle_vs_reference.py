@@ -60,3 +60,24 @@ def test_eval_mode_encoders_match_reference():
                  (mid["attns"][0]["soft_attn"], omid["attns"][0]["soft_attn"]),
                  (mid["attns"][0]["hard_attn"], omid["attns"][0]["hard_attn"])):
         assert float((a - b).abs().max()) < 1e-5
+
+
+@pytest.mark.parametrize("hw", [(128, 128), (64, 256), (256, 64)])
+def test_eval_mode_other_resolutions_match_reference(hw):
+    """Eval-mode encode_image at input sizes other than the training resolution: the reference interpolates the
+    positional table bicubically (modules/module_clip_vtransformer.py:35-53).  SegViT takes its semantic (non-MAE) branch only
+    for n or 4 n patch tokens (modules/module_seg_vit.py:423), so the only other sizes the reference supports have 4x the
+    tokens: twice the resolution, or a rectangle with the same area.  Toy grid 4 x 4 -> 8 x 8, 4 x 16, 16 x 4."""
+    cfg = so.toy_config()
+    model = rh.build_reference_model(cfg)
+    params = so.init_params(cfg, seed=43)
+    model.load_state_dict(params, strict=False)
+    model.eval()
+    img = torch.randn(2, 3, hw[0], hw[1], generator=torch.Generator().manual_seed(44))
+    with torch.no_grad():
+        x, hid, mid = model.clip.encode_image(img, return_hidden=True)
+        ox, ohid, omid = so.encode_image_eval(img, params, cfg, kv_layout="torch18_flat")
+    model.train()
+    for a, b in ((x, ox), (hid, ohid), (mid["hidden"], omid["hidden"]),
+                 (mid["attns"][0]["soft_attn"], omid["attns"][0]["soft_attn"])):
+        assert a.shape == b.shape and float((a - b).abs().max()) < 1e-5

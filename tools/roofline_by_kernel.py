@@ -3,8 +3,8 @@
     python tools/roofline_by_kernel.py profiles/r1_step_breakdown_cuda_events.txt > profiles/r1_roofline_by_kernel.txt
 
 GEMM: algorithmic 2*M*N*K; attention: 4*B*H*Lq*Lk*hd forward, 2.5x that backward (5 products instead of 2), dense (causal
-not halved, SURVEY 8(d) convention); LayerNorm: algorithmic bytes/row = D*(4+2) forward, D*(2+4+4+4+2) backward
-(DESIGN.md section 3).  Peaks: MEASURED_PEAKS.json (sustained bf16 cuBLAS, HBM copy)."""
+not halved, SURVEY 8(d) convention); LayerNorm: algorithmic bytes/row = D*(4+2) forward, D*(2+4+2+2) backward
+(bf16 gradient stream).  Peaks: MEASURED_PEAKS.json (sustained bf16 cuBLAS, HBM copy)."""
 import json
 import os
 import re
@@ -28,7 +28,7 @@ for line in open(sys.argv[1]):
         fl = 4.0 * kv["B"] * kv["H"] * kv["Lq"] * kv["Lk"] * kv["hd"] * cnt * (2.5 if "bwd" in desc else 1.0)
         rows.append((ms, "%s %s" % (ph, desc), "tensor", fl / ms / 1e9, TF, "TFLOP/s"))
     elif desc.startswith("sc_layernorm"):
-        by = kv["rows"] * kv["D"] * (16.0 if "bwd" in desc else 6.0) * cnt
+        by = kv["rows"] * kv["D"] * (10.0 if "bwd" in desc else 6.0) * cnt      # bwd: dy bf16 + x fp32 + bf16 gradient stream read-modify-write
         rows.append((ms, "%s %s" % (ph, desc), "hbm", by / ms / 1e6, GB, "GB/s"))
 tot = sum(r[0] for r in rows)
 print("# per-kernel roofline (one step, batch 256, ViT-B/16 contrastive); peaks: %.1f TFLOP/s sustained bf16, %.0f GB/s HBM" % (TF, GB))
