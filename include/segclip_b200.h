@@ -195,6 +195,12 @@ typedef struct {
   void* d_k;
   void* d_v;
   float* delta_ws; /* fp32 scratch [B, H, Lq] (rowsum(dO o O)); required by the tensor-core kernels */
+  /* optional fp32 [H*hd] each (all three or none): += column sums over all rows of d_q / d_k / d_v -- the bias gradient of
+   * the projection that produced q, k, v (in_proj_bias, modules/module_seg_vit.py:189), fused into the kernel that writes
+   * them (tcgen05 path: from the staged output tiles; other paths: a column-sum launch after the kernels) */
+  float* dq_colsum;
+  float* dk_colsum;
+  float* dv_colsum;
 } sc_attn_bwd_desc;
 int sc_attention_bwd(const sc_attn_bwd_desc* g, void* stream);
 

@@ -275,17 +275,37 @@ extern "C" int sc_attention_fwd(const sc_attn_desc* a, void* stream) {
   return SC_OK;
 }
 
+extern "C" int sc_colsum(const void* x, int dtype, int64_t ld, int64_t rows, int cols, float* out, void* stream);
+
+// bias-gradient column sums of d_q / d_k / d_v for the paths whose kernels do not produce them (sample-major packed rows)
+static int colsum_after(const sc_attn_bwd_desc* g, cudaStream_t st) {
+  const sc_attn_desc* a = &g->fwd;
+  if (!g->dq_colsum) return SC_OK;
+  const int W = a->H * a->hd;
+  SC_CHECK_ARG(a->q_bs == (long)a->Lq * a->q_rs && a->k_bs == (long)a->Lk * a->k_rs && a->v_bs == (long)a->Lk * a->v_rs,
+               "sc_attention_bwd: fused bias-gradient column sums need sample-major packed q / k / v");
+  int rc;
+  if ((rc = sc_colsum(g->d_q, a->dtype, a->q_rs, (int64_t)a->B * a->Lq, W, g->dq_colsum, st))) return rc;
+  if ((rc = sc_colsum(g->d_k, a->dtype, a->k_rs, (int64_t)a->B * a->Lk, W, g->dk_colsum, st))) return rc;
+  return sc_colsum(g->d_v, a->dtype, a->v_rs, (int64_t)a->B * a->Lk, W, g->dv_colsum, st);
+}
+
 extern "C" int sc_attention_bwd(const sc_attn_bwd_desc* g, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
   const sc_attn_desc* a = &g->fwd;
   int rc = check_desc(a, "sc_attention_bwd");
   if (rc) return rc;
   SC_CHECK_ARG(g->d_o && g->d_q && g->d_k && g->d_v && a->lse, "sc_attention_bwd: null pointer");
+  SC_CHECK_ARG((g->dq_colsum != nullptr) == (g->dk_colsum != nullptr) && (g->dq_colsum != nullptr) == (g->dv_colsum != nullptr),
+               "sc_attention_bwd: dq/dk/dv_colsum come together");
   {
     static const int use_tc = [] { const char* e = getenv("SC_ATT_TC"); return e ? atoi(e) : 1; }();
     if (use_tc && !a->force_generic && g->delta_ws && sc_attn_tc_supported(a)) return sc_attention_bwd_tc(g, g->delta_ws, st);
   }
-  if (!a->force_generic && g->delta_ws && sc_attn_mma_supported(a)) return sc_attention_bwd_mma(g, g->delta_ws, st);
+  if (!a->force_generic && g->delta_ws && sc_attn_mma_supported(a)) {
+    if ((rc = sc_attention_bwd_mma(g, g->delta_ws, st))) return rc;
+    return colsum_after(g, st);
+  }
   const size_t smem_q = sizeof(float) * ((size_t)2 * a->Lk * (a->hd + 1) + (size_t)ATT_WARPS * a->Lk + 2 * ATT_WARPS * 64);
   const size_t smem_kv = sizeof(float) * ((size_t)2 * a->Lq * (a->hd + 1) + 2 * (size_t)a->Lq +
                                           2 * (size_t)ATT_WARPS * a->Lq + 2 * ATT_WARPS * 64);
@@ -303,5 +323,5 @@ extern "C" int sc_attention_bwd(const sc_attn_bwd_desc* g, void* stream) {
     attn_bwd_dkv_kernel<bf16><<<grid, ATT_THREADS, smem_kv, st>>>(*g);
   }
   SC_LAUNCH_CHECK();
-  return SC_OK;
+  return colsum_after(g, st);
 }

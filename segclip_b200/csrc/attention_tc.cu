@@ -387,6 +387,39 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       }
       return live;
     };
+    // bias gradient of the q / k / v projection = column sums of dQ / dK / dV over all rows: taken from the staged bf16 box
+    // (rows past L hold exact zeros: their P / dS entries are masked), transposed read-back like the GEMM epilogue's
+    auto box_colsum = [&](float* out, bool live, int col0) {
+      if (out == nullptr || !live) return;              // warp-uniform
+      __syncwarp();
+      const int c4 = lane & 3;
+      float cs[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) cs[k] = 0.f;
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        const int rr = 8 * t + (lane >> 2);
+        const uint4 u = lds128b(estage + rr * 64 + ((c4 ^ ((rr >> 1) & 3)) << 4));
+        const uint32_t uw[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const float2 x = unpack2_bf16(uw[k]);
+          cs[2 * k] += x.x;
+          cs[2 * k + 1] += x.y;
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        cs[k] += __shfl_xor_sync(0xffffffffu, cs[k], 4);
+        cs[k] += __shfl_xor_sync(0xffffffffu, cs[k], 8);
+        cs[k] += __shfl_xor_sync(0xffffffffu, cs[k], 16);
+      }
+      if (lane < 4) {
+        float* o = out + col0 + c4 * 8;
+        asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(o), "f"(cs[0]), "f"(cs[1]), "f"(cs[2]), "f"(cs[3]) : "memory");
+        asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(o + 4), "f"(cs[4]), "f"(cs[5]), "f"(cs[6]), "f"(cs[7]) : "memory");
+      }
+    };
     auto release_and_store = [&](const CUtensorMap* map, bool live, int col0, int row0, int b) {
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       __syncwarp();
@@ -411,6 +444,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_dkv_free);
       release_and_store(map, row0 < L, h * HD + (cg & 1) * 32, row0, b);
+      box_colsum(cg < 2 ? gd.dv_colsum : gd.dk_colsum, row0 < L, h * HD + (cg & 1) * 32);
     };
     auto dq_epilogue = [&](int h, int b) {
       // dQ (TMEM lanes = queries): bar_dkv of the item's last key tile was committed after every MMA of the item;
@@ -423,6 +457,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_dq_free);
       release_and_store(&tmGQ, live, h * HD + (cg & 1) * 32, row0, b);
+      box_colsum(gd.dq_colsum, live, h * HD + (cg & 1) * 32);
     };
     // The read-out of an item's last dV / dK and of its dQ is deferred until this warp has delivered the first tile of
     // the NEXT item, so the MMA pipe never waits for the drain (the control warp holds the next item's accumulating

@@ -406,8 +406,11 @@ class Engine:
             grp_mlp = mlp(x_mid, x_out, dx, dxT, pre, nm, tag, eps, act, bo_grad=self.grads[pre + nm["bo"]] if fuse_ln else None)
             d_att, dqkv, d_ln = sbuf("d_att", (M, D), T), sbuf("dqkv", (M, 3 * D), T), sbuf("d_ln", (M, D), T)
             grp = linear_bwd(dxT, att, pre + nm["wo"], None if fuse_ln else pre + nm["bo"], dx=d_att)
-            grp.append(ops.attention_bwd_op(ad, d_att, dqkv, dqkv[:, D:], dqkv[:, 2 * D:], sbuf("att_delta", (Bn, H, Lseq), f32)))
-            grp += linear_bwd(dqkv, h1, pre + nm["wqkv"], pre + nm["bqkv"], dx=d_ln)
+            # in_proj bias gradient = column sums of dQ | dK | dV: produced by the attention backward that writes them
+            fuse_qkv_bias = is_bf16 and not os.environ.get("SC_NO_FUSE_QKV_BIAS")
+            grp.append(ops.attention_bwd_op(ad, d_att, dqkv, dqkv[:, D:], dqkv[:, 2 * D:], sbuf("att_delta", (Bn, H, Lseq), f32),
+                                            bias_grad=self.grads[pre + nm["bqkv"]] if fuse_qkv_bias else None))
+            grp += linear_bwd(dqkv, h1, pre + nm["wqkv"], None if fuse_qkv_bias else pre + nm["bqkv"], dx=d_ln)
             prev_b2 = None
             if prev is not None and fuse_ln:          # take over the previous block's c_proj bias gradient
                 prev["group"].remove(prev["colsum"])

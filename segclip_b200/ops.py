@@ -152,10 +152,16 @@ def attention_op(a, keep=()):
     return Op("sc_attention_fwd", (C.byref(a),), (a, keep))
 
 
-def attention_bwd_op(a, d_o, d_q, d_k, d_v, delta_ws=None, keep=()):
+def attention_bwd_op(a, d_o, d_q, d_k, d_v, delta_ws=None, keep=(), bias_grad=None):
+    """bias_grad: optional fp32 [3*H*hd] gradient of the fused q|k|v projection bias (+= column sums of d_q, d_k, d_v)."""
     g = L.AttnBwdDesc()
     g.fwd = a
     g.d_o, g.d_q, g.d_k, g.d_v = d_o.data_ptr(), d_q.data_ptr(), d_k.data_ptr(), d_v.data_ptr()
+    if bias_grad is not None:
+        W = a.H * a.hd
+        assert bias_grad.dtype == torch.float32 and bias_grad.numel() == 3 * W and bias_grad.is_contiguous()
+        g.dq_colsum, g.dk_colsum, g.dv_colsum = bias_grad.data_ptr(), bias_grad.data_ptr() + 4 * W, bias_grad.data_ptr() + 8 * W
+        keep = (keep, bias_grad)
     if delta_ws is not None:
         assert delta_ws.dtype == torch.float32 and delta_ws.numel() >= a.B * a.H * a.Lq
         g.delta_ws = delta_ws.data_ptr()

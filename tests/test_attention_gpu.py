@@ -35,8 +35,13 @@ def _run(B, H, L, hd, dtype, causal=False, force_generic=False, seed=0, ramp=0.0
     ops.attention_op(a)()
     dqkv = torch.full_like(qkv, float("nan"))
     delta = torch.empty(B, H, L, device="cuda")
-    ops.attention_bwd_op(a, do, dqkv, dqkv[:, D:], dqkv[:, 2 * D:], delta)()
+    bias_grad = torch.full((3 * D,), 0.5, device="cuda") if dtype == torch.bfloat16 else None      # accumulates (+=)
+    ops.attention_bwd_op(a, do, dqkv, dqkv[:, D:], dqkv[:, 2 * D:], delta, bias_grad=bias_grad)()
     torch.cuda.synchronize()
+    if bias_grad is not None and check_bwd:
+        # in_proj bias gradient fused into the backward: column sums of the dQ | dK | dV it stored
+        want = dqkv.float().sum(0) + 0.5
+        assert float((bias_grad - want).abs().max()) <= 2e-3 * (1.0 + float(want.abs().max())), "fused bias-gradient column sums"
     v4 = qkv.view(B, L, 3, H, hd)
     ro, rl, rq, rk, rv = _ref(v4[:, :, 0], v4[:, :, 1], v4[:, :, 2], do.view(B, L, H, hd), causal)
     tol = 2e-5 if dtype == torch.float32 else 2e-2
