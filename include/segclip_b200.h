@@ -106,6 +106,13 @@ typedef struct {
   float* colsum_out;     /* optional fp32 [N]: colsum_out[n] += sum_m C[m,n] (bias gradient fused into the dgrad that produces dY);
                             only with bf16 C on the tensor-core path */
   int32_t residual_dtype; /* SC_F32 (default) or SC_BF16 */
+  /* optional per-head row dots of the result with a second matrix (bf16 C on the tensor-core path, head dim 64):
+   *   dot_out[((m / dot_L) * (N / 64) + n / 64) * dot_L + m % dot_L] = sum over the 64 columns of head n / 64 of C[m,:] * dot_aux[m,:]
+   * i.e. delta = rowsum(dO o O) of the attention backward (modules/module_seg_vit.py:189), produced by the out_proj dgrad
+   * that computes dO instead of a separate pass over dO and O.  dot_aux: bf16 [M, N], leading dimension ldc. */
+  const void* dot_aux;
+  float* dot_out;
+  int32_t dot_L;
 } sc_gemm_desc;
 
 int sc_gemm(const sc_gemm_desc* d, void* stream);
@@ -201,6 +208,7 @@ typedef struct {
   float* dq_colsum;
   float* dk_colsum;
   float* dv_colsum;
+  int32_t delta_ready; /* delta_ws already holds rowsum(dO o O) (written by sc_gemm's dot_out): skip the delta pass */
 } sc_attn_bwd_desc;
 int sc_attention_bwd(const sc_attn_bwd_desc* g, void* stream);
 

@@ -1019,6 +1019,15 @@ bool sc_attn_tc_supported(const sc_attn_desc* a) {
          packed(a->v, a->v_bs, a->v_rs, a->Lk) && packed(a->o, a->o_bs, a->o_rs, a->Lq);
 }
 
+// delta[b,h,i] = sum_d dO[b,i,h,d] O[b,i,h,d] (head dim 64) as a stand-alone pass; used by sc_gemm for dot_out when its kernel
+// cannot fuse the dots
+int sc_attn_delta(const void* o, const void* d_o, long bs, long rs, int B, int H, int L, float* delta, cudaStream_t st) {
+  const long n = (long)B * L * H;
+  attn_delta_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>((const bf16*)o, (const bf16*)d_o, bs, rs, B, H, L, delta);
+  SC_LAUNCH_CHECK();
+  return SC_OK;
+}
+
 int sc_attention_bwd_tc(const sc_attn_bwd_desc* g, float* delta, cudaStream_t st) {
   const sc_attn_desc* a = &g->fwd;
   const int L = a->Lq;
@@ -1035,10 +1044,12 @@ int sc_attention_bwd_tc(const sc_attn_bwd_desc* g, float* delta, cudaStream_t st
   if ((rc = sc_get_tensor_map_3d(g->d_q, (uint64_t)a->H * HD, L, a->B, a->q_rs, a->q_bs, 32, 32, 64, &gq))) return rc;
   if ((rc = sc_get_tensor_map_3d(g->d_k, (uint64_t)a->H * HD, L, a->B, a->k_rs, a->k_bs, 32, 32, 64, &gk))) return rc;
   if ((rc = sc_get_tensor_map_3d(g->d_v, (uint64_t)a->H * HD, L, a->B, a->v_rs, a->v_bs, 32, 32, 64, &gv))) return rc;
-  sc_count_kernel(SC_K_ATTN_BWD_TC, 2);
-  const long n = rows * a->H;
-  attn_delta_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>((const bf16*)a->o, (const bf16*)g->d_o, a->o_bs, a->o_rs, a->B,
-                                                                 a->H, L, delta);
+  sc_count_kernel(SC_K_ATTN_BWD_TC, g->delta_ready ? 1 : 2);
+  if (!g->delta_ready) {         // (otherwise the out_proj dgrad that produced dO has already written it: sc_gemm dot_out)
+    const long n = rows * a->H;
+    attn_delta_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>((const bf16*)a->o, (const bf16*)g->d_o, a->o_bs, a->o_rs, a->B,
+                                                                   a->H, L, delta);
+  }
   const long items = (long)a->H * a->B;
   dim3 grid((unsigned)(items < sc_num_sms() ? items : sc_num_sms()));       // persistent: one CTA per SM
   if (a->causal) {

@@ -26,6 +26,8 @@ struct EpiParams {
   int mul_aux_dtype;
   int mul_aux_act;
   float* colsum_out;
+  float* dot_out;       // per-head row dots with the aux tile (see sc_gemm_desc.dot_out)
+  int dot_L;
 };
 
 static inline EpiParams make_epi(const sc_gemm_desc* d) {
@@ -53,6 +55,8 @@ static inline EpiParams make_epi(const sc_gemm_desc* d) {
   p.mul_aux_dtype = d->mul_aux_dtype;
   p.mul_aux_act = d->mul_aux_act;
   p.colsum_out = d->colsum_out;
+  p.dot_out = d->dot_out;
+  p.dot_L = d->dot_L;
   return p;
 }
 

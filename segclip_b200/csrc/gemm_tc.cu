@@ -386,9 +386,31 @@ int launch(const sc_gemm_desc* d, const CUtensorMap& ta, const CUtensorMap& tb, 
 extern void sc_count_kernel(int kind, int n);
 int sc_gemm_tc2(const sc_gemm_desc* d, cudaStream_t st);
 
+// set by the 2-CTA launcher when the per-head row dots (sc_gemm_desc.dot_out) were fused into the epilogue
+bool& sc_gemm_dot_fused() {
+  static thread_local bool f = false;
+  return f;
+}
+int sc_attn_delta(const void* o, const void* d_o, long bs, long rs, int B, int H, int L, float* delta, cudaStream_t st);
+static int sc_gemm_tc_impl(const sc_gemm_desc* d, cudaStream_t st);
+
 // Returns SC_ERR_UNSUPPORTED when the problem does not meet the TMA alignment rules (caller falls
 // back to the FMA kernel only in fp32 mode; in bf16 mode this is an error).
 int sc_gemm_tc(const sc_gemm_desc* d, cudaStream_t st) {
+  if (!d->dot_out) return sc_gemm_tc_impl(d, st);
+  if (!(d->dot_aux && d->dot_L > 0 && d->M % d->dot_L == 0 && d->N % 64 == 0 && d->c_dtype == SC_BF16 && !d->accumulate)) {
+    sc_set_error("sc_gemm: dot_out needs dot_aux, dot_L dividing M, N %% 64 == 0 and a bf16 C");
+    return SC_ERR_INVALID;
+  }
+  sc_gemm_dot_fused() = false;
+  int rc = sc_gemm_tc_impl(d, st);
+  if (rc) return rc;
+  if (sc_gemm_dot_fused()) return SC_OK;
+  // kernels without the fused epilogue (1-CTA tiles, other operand layouts): one pass over C and dot_aux after the GEMM
+  return sc_attn_delta(d->dot_aux, d->C, (long)d->dot_L * d->ldc, d->ldc, d->M / d->dot_L, d->N / 64, d->dot_L, d->dot_out, st);
+}
+
+static int sc_gemm_tc_impl(const sc_gemm_desc* d, cudaStream_t st) {
   const bool a_mn = d->trans_a != 0, b_mn = d->trans_b != 0;
   auto aligned16 = [](const void* p) { return ((uintptr_t)p & 15) == 0; };
   if (!(d->lda % 8 == 0 && d->ldb % 8 == 0 && aligned16(d->A) && aligned16(d->B) && d->N % 8 == 0 &&

@@ -206,6 +206,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     const uint32_t stage = smem_u32(epi_stage) + warp * EPI2_STAGE_BYTES;
     uint32_t g = 0;
     uint32_t aux_phase = 0;          // bit c: parity of this warp's input-tile barrier c
+    float dotacc = 0.f;              // EF_ROWDOT: running per-head row dot of this lane's row
     int it = 0;
     for (int item = pair; item < num_items; item += npairs, ++it) {
       const int nt = item % tiles_n;
@@ -243,7 +244,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             const int bx = c % NBOX;
             mbar_wait(&aux_bar[warp * 4 + bx], (aux_phase >> bx) & 1u);
             aux_phase ^= 1u << bx;
-            if constexpr (kAux) epi_finish_aux_tma<EF>(ep, v, stage + bx * BOXB, lane, mrow0, n0, c, breg, &tmC);
+            if constexpr (kAux) epi_finish_aux_tma<EF>(ep, v, stage + bx * BOXB, lane, mrow0, n0, c, breg, &tmC, dotacc);
             else epi_finish_res_tma<EF>(ep, v, stage + bx * BOXB, lane, mrow0, n0, c, breg, &tmC);
             if (NBOX < 4 && c + NBOX < 4 && n0 + NBOX * 32 < ep.N) {      // box reused within the tile (fp32 boxes)
               bulk_wait_read<0>();
@@ -286,6 +287,7 @@ int launch2(const sc_gemm_desc* d, const CUtensorMap& ta, const CUtensorMap& tb,
     int rc;
     if ((rc = sc_get_tensor_map_sw(d->C, d->N, d->M, d->ldc, 32, 32, 64, &tc_))) return rc;
     if constexpr ((EF & EF_RESID_BF) != 0) rc = sc_get_tensor_map_sw(d->residual, d->N, d->M, d->ldr, 32, 32, 64, &tx_);
+    else if constexpr ((EF & EF_ROWDOT) != 0) rc = sc_get_tensor_map_sw(d->dot_aux, d->N, d->M, d->ldc, 32, 32, 64, &tx_);
     else rc = sc_get_tensor_map_sw(d->mul_aux, d->N, d->M, d->ldc, 32, 32, 64, &tx_);
     if (rc) return rc;
   }
@@ -325,6 +327,7 @@ int launch2(const sc_gemm_desc* d, const CUtensorMap& ta, const CUtensorMap& tb,
 }  // namespace
 
 extern void sc_count_kernel(int kind, int n);
+bool& sc_gemm_dot_fused();
 
 // Same contract as sc_gemm_tc; the caller has already validated alignment.  Returns SC_ERR_UNSUPPORTED when the shape is
 // a poor fit for 256 x 256 pair tiles (the 1-CTA kernel then runs).
@@ -369,6 +372,10 @@ int sc_gemm_tc2(const sc_gemm_desc* d, cudaStream_t st) {
     SC_L2(false, false, EF_GENERIC)
   }
   if (!a_mn && b_mn) {
+    if (ef == 0 && d->dot_out) {
+      sc_gemm_dot_fused() = true;
+      SC_L2(false, true, EF_ROWDOT)
+    }
     if (ef == 0) SC_L2(false, true, 0)
     if (ef == EF_MULAUX_QGELU) SC_L2(false, true, EF_MULAUX_QGELU)
     if (ef == EF_MULAUX_GELU) SC_L2(false, true, EF_MULAUX_GELU)

@@ -148,6 +148,7 @@ enum : int {
   EF_MULAUX_GELU = 256, // * GELU'(aux)
   EF_ACCUM = 512,       // C += result (fp32 read-modify-write, single split; old C prefetched like a residual)
   EF_RESID_BF = 1024,   // + residual (bf16), bf16 output: the bf16 residual stream (2-CTA kernel: residual tile through the TMA)
+  EF_ROWDOT = 2048,     // plain bf16 output + per-head row dots with a second bf16 tile (attention delta from the out_proj dgrad)
   EF_GENERIC = 1 << 20
 };
 
@@ -426,13 +427,13 @@ struct EpiTma {
 // tile start (while the tile's main loop still runs) on one mbarrier each.
 template <int EF>
 struct EpiAuxTma {
-  static constexpr bool value = (EF != EF_GENERIC) && (EF & (EF_RESID_BF | EF_MULAUX_QGELU | EF_MULAUX_GELU)) != 0 &&
+  static constexpr bool value = (EF != EF_GENERIC) && (EF & (EF_RESID_BF | EF_MULAUX_QGELU | EF_MULAUX_GELU | EF_ROWDOT)) != 0 &&
                                 (EF & (EF_OUT_F32 | EF_ATOMIC | EF_RESID | EF_C2)) == 0;
 };
 
 template <int EF>
 SC_DEVINL void epi_finish_aux_tma(const EpiParams& ep, float (&v)[32], uint32_t box, int lane, int mrow0, int n0, int c,
-                                  const float4& breg, const CUtensorMap* tmC) {
+                                  const float4& breg, const CUtensorMap* tmC, float& dotacc) {
   if constexpr ((EF & EF_BIAS) != 0) {
     const int src = c * 8;
 #pragma unroll
@@ -458,6 +459,7 @@ SC_DEVINL void epi_finish_aux_tma(const EpiParams& ep, float (&v)[32], uint32_t 
       if constexpr ((EF & EF_RESID_BF) != 0) { o0 += x.x; o1 += x.y; }
       if constexpr ((EF & EF_MULAUX_QGELU) != 0) { o0 *= qgelu_grad_fast(x.x); o1 *= qgelu_grad_fast(x.y); }
       if constexpr ((EF & EF_MULAUX_GELU) != 0) { o0 *= act_grad(x.x, SC_ACT_GELU_ERF); o1 *= act_grad(x.y, SC_ACT_GELU_ERF); }
+      if constexpr ((EF & EF_ROWDOT) != 0) dotacc = fmaf(o0, x.x, fmaf(o1, x.y, dotacc));
       ow[k] = pack2_bf16(o0, o1);
     }
     sts128b(a, make_uint4(ow[0], ow[1], ow[2], ow[3]));
@@ -466,6 +468,17 @@ SC_DEVINL void epi_finish_aux_tma(const EpiParams& ep, float (&v)[32], uint32_t 
   __syncwarp();
   tma_store_2d(tmC, box, n0, mrow0);
   bulk_commit();
+  if constexpr ((EF & EF_ROWDOT) != 0) {
+    // chunks come in pairs per 64-column head (tile column offsets are multiples of 128): the odd chunk completes the dot
+    if (c & 1) {
+      const int m = mrow0 + lane;
+      if (m < ep.M) {
+        const int b = m / ep.dot_L, l = m - b * ep.dot_L;
+        ep.dot_out[((long)b * (ep.N >> 6) + (n0 >> 6)) * ep.dot_L + l] = dotacc;
+      }
+      dotacc = 0.f;
+    }
+  }
   if (ep.colsum_out) {                                 // uniform branch: column sums of what was stored (bias gradient)
     // rows >= M and columns >= N hold exact zeros (zero-filled operands and input tile), so no row mask is needed
     const int c4 = lane & 3, n = n0 + c4 * 8;

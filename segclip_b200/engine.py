@@ -324,7 +324,7 @@ class Engine:
 
         # ---------------- generic layers
         def linear_bwd(dy, x, wname, bname, dx=None, dx_acc=False, wslice=None, bslice=None, mul_aux=None, mul_act=0,
-                       dx_colsum=None, simt=False):
+                       dx_colsum=None, simt=False, dot=None):
             w = self.W(wname)
             gw = self.Gr(wname)
             gb = self.grads[bname] if bname else None
@@ -334,8 +334,9 @@ class Engine:
                 gb = gb[bslice]
             grp = []
             if dx is not None:
+                dkw = dict(dot_aux=dot[0], dot_out=dot[1], dot_L=dot[2]) if dot is not None else {}
                 grp.append(ops.gemm_op(dy, w, dx, trans_b=True, accumulate=dx_acc, mul_aux=mul_aux, mul_aux_act=mul_act,
-                                       colsum_out=dx_colsum, force_simt=simt))
+                                       colsum_out=dx_colsum, force_simt=simt, **dkw))
             grp.append(ops.gemm_op(dy, x, gw, trans_a=True, trans_b=True, accumulate=True, split_k=0 if simt else -1,
                                    force_simt=simt))
             if gb is not None:
@@ -405,11 +406,15 @@ class Engine:
             fuse_ln = not os.environ.get("SC_NO_FUSE_LN_COLSUM")
             grp_mlp = mlp(x_mid, x_out, dx, dxT, pre, nm, tag, eps, act, bo_grad=self.grads[pre + nm["bo"]] if fuse_ln else None)
             d_att, dqkv, d_ln = sbuf("d_att", (M, D), T), sbuf("dqkv", (M, 3 * D), T), sbuf("d_ln", (M, D), T)
-            grp = linear_bwd(dxT, att, pre + nm["wo"], None if fuse_ln else pre + nm["bo"], dx=d_att)
+            # delta = rowsum(dO o O) of the attention backward comes out of the out_proj dgrad that computes dO (head dim 64)
+            att_delta = sbuf("att_delta", (Bn, H, Lseq), f32)
+            fuse_delta = is_bf16 and hd == 64 and not os.environ.get("SC_NO_FUSE_DELTA")
+            grp = linear_bwd(dxT, att, pre + nm["wo"], None if fuse_ln else pre + nm["bo"], dx=d_att,
+                             dot=(att, att_delta, Lseq) if fuse_delta else None)
             # in_proj bias gradient = column sums of dQ | dK | dV: produced by the attention backward that writes them
             fuse_qkv_bias = is_bf16 and not os.environ.get("SC_NO_FUSE_QKV_BIAS")
-            grp.append(ops.attention_bwd_op(ad, d_att, dqkv, dqkv[:, D:], dqkv[:, 2 * D:], sbuf("att_delta", (Bn, H, Lseq), f32),
-                                            bias_grad=self.grads[pre + nm["bqkv"]] if fuse_qkv_bias else None))
+            grp.append(ops.attention_bwd_op(ad, d_att, dqkv, dqkv[:, D:], dqkv[:, 2 * D:], att_delta,
+                                            bias_grad=self.grads[pre + nm["bqkv"]] if fuse_qkv_bias else None, delta_ready=fuse_delta))
             grp += linear_bwd(dqkv, h1, pre + nm["wqkv"], None if fuse_qkv_bias else pre + nm["bqkv"], dx=d_ln)
             prev_b2 = None
             if prev is not None and fuse_ln:          # take over the previous block's c_proj bias gradient

@@ -36,7 +36,7 @@ def _p(t):
 
 def gemm_desc(A, B, C_, *, trans_a=False, trans_b=False, bias=None, rowbias=None, rowbias_idx=None, rowbias_mod=0,
               act=ACT_NONE, residual=None, C2=None, accumulate=False, split_k=0, alpha=1.0, force_simt=False,
-              mul_aux=None, mul_aux_act=ACT_NONE, colsum_out=None):
+              mul_aux=None, mul_aux_act=ACT_NONE, colsum_out=None, dot_aux=None, dot_out=None, dot_L=0):
     """sc_gemm descriptor for C = epi(A B^T); see include/segclip_b200.h."""
     for t in (A, B, C_):
         _chk2d(t)
@@ -82,6 +82,11 @@ def gemm_desc(A, B, C_, *, trans_a=False, trans_b=False, bias=None, rowbias=None
     if colsum_out is not None:
         assert colsum_out.dtype == torch.float32 and colsum_out.numel() == N and C_.dtype == torch.bfloat16
         d.colsum_out = colsum_out.data_ptr()
+    if dot_out is not None:
+        _chk2d(dot_aux)
+        assert dot_aux.shape == C_.shape and dot_aux.stride(0) == C_.stride(0) and dot_aux.dtype == C_.dtype == torch.bfloat16
+        assert dot_out.dtype == torch.float32 and dot_out.numel() == M * (N // 64) and dot_L > 0 and M % dot_L == 0
+        d.dot_aux, d.dot_out, d.dot_L = dot_aux.data_ptr(), dot_out.data_ptr(), dot_L
     return d
 
 
@@ -152,8 +157,9 @@ def attention_op(a, keep=()):
     return Op("sc_attention_fwd", (C.byref(a),), (a, keep))
 
 
-def attention_bwd_op(a, d_o, d_q, d_k, d_v, delta_ws=None, keep=(), bias_grad=None):
-    """bias_grad: optional fp32 [3*H*hd] gradient of the fused q|k|v projection bias (+= column sums of d_q, d_k, d_v)."""
+def attention_bwd_op(a, d_o, d_q, d_k, d_v, delta_ws=None, keep=(), bias_grad=None, delta_ready=False):
+    """bias_grad: optional fp32 [3*H*hd] gradient of the fused q|k|v projection bias (+= column sums of d_q, d_k, d_v);
+    delta_ready: delta_ws already holds rowsum(dO o O) (gemm_op(..., dot_out=delta_ws))."""
     g = L.AttnBwdDesc()
     g.fwd = a
     g.d_o, g.d_q, g.d_k, g.d_v = d_o.data_ptr(), d_q.data_ptr(), d_k.data_ptr(), d_v.data_ptr()
@@ -165,6 +171,7 @@ def attention_bwd_op(a, d_o, d_q, d_k, d_v, delta_ws=None, keep=(), bias_grad=No
     if delta_ws is not None:
         assert delta_ws.dtype == torch.float32 and delta_ws.numel() >= a.B * a.H * a.Lq
         g.delta_ws = delta_ws.data_ptr()
+        g.delta_ready = int(delta_ready)
     return Op("sc_attention_bwd", (C.byref(g),), (g, d_o, d_q, d_k, d_v, delta_ws, keep))
 
 

@@ -238,3 +238,24 @@ def test_tc2_fp32_residual_guard_band():
     ref = A.float() @ B.float().t() + bias + res
     assert float((C - ref).abs().max() / ref.abs().max()) < 2e-4
     assert bool((big[M:] == 7.0).all())
+
+
+@pytest.mark.parametrize("B,L", [(8, 197), (2, 196), (6, 77), (40, 196)])
+def test_dgrad_with_fused_attention_delta(B, L):
+    """out_proj dgrad dO = dY W with the per-head row dots delta[b,h,l] = sum_d dO[b,l,h,d] O[b,l,h,d] fused into the
+    epilogue (2-CTA kernel: O tile TMA-loaded into the staging box; M < 512: stand-alone pass after the 1-CTA GEMM)."""
+    from segclip_b200 import ops
+    torch.manual_seed(B)
+    M, N, K = B * L, 768, 768
+    H = N // 64
+    dy = torch.randn(M, K, device="cuda").bfloat16()
+    W = (torch.randn(K, N, device="cuda") * 0.05).bfloat16()
+    O = torch.randn(M, N, device="cuda").bfloat16()
+    dO = torch.full((M, N), float("nan"), device="cuda", dtype=torch.bfloat16)
+    delta = torch.full((B, H, L), float("nan"), device="cuda")
+    ops.gemm(dy, W, dO, trans_b=True, dot_aux=O, dot_out=delta, dot_L=L)
+    torch.cuda.synchronize()
+    ref = dy.float() @ W.float()
+    assert float((dO.float() - ref).abs().max() / ref.abs().max()) < 1e-2
+    want = (ref * O.float()).view(B, L, H, 64).sum(-1).permute(0, 2, 1)
+    assert float((delta - want).abs().max()) < 2e-2 * float(want.abs().max())
