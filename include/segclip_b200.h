@@ -35,6 +35,7 @@ extern "C" {
 #define SC_ACT_NONE 0
 #define SC_ACT_QUICKGELU 1 /* x*sigmoid(1.702x): modules/module_clip_util.py:134-136 */
 #define SC_ACT_GELU_ERF 2  /* nn.GELU():        modules/module_seg_vit.py:128, module_mae.py:151 */
+#define SC_ACT_DERIV 3     /* mul_aux_act only: mul_aux already holds act'(pre-activation), see c2_is_act_grad */
 
 #define SC_ABI_VERSION 1
 
@@ -113,6 +114,10 @@ typedef struct {
   const void* dot_aux;
   float* dot_out;
   int32_t dot_L;
+  /* forward of an activated Linear whose backward is fused into the next dgrad: C2 receives act'(v) instead of the
+   * pre-activation v (the epilogue has the sigmoid / erf at hand; the backward then multiplies with mul_aux_act =
+   * SC_ACT_DERIV instead of re-evaluating the derivative for every element) */
+  int32_t c2_is_act_grad;
 } sc_gemm_desc;
 
 int sc_gemm(const sc_gemm_desc* d, void* stream);

@@ -91,6 +91,7 @@ SC_DEVINL float act_fwd(float x, int act) {
   return x;
 }
 SC_DEVINL float act_grad(float x, int act) {
+  if (act == SC_ACT_DERIV) return x;          // x already is the derivative (stored by the forward epilogue)
   if (act == SC_ACT_QUICKGELU) {
     float s = __fdividef(1.0f, 1.0f + __expf(-1.702f * x));
     return s * (1.0f + 1.702f * x * (1.0f - s));

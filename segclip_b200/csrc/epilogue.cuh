@@ -20,6 +20,7 @@ struct EpiParams {
   int c_dtype;
   void* C2;
   int c2_dtype;
+  int c2_is_act_grad;   // C2 := act'(v) instead of v
   int accumulate;
   int atomic;  // accumulate with atomics (split-K)
   const void* mul_aux;  // optional: v *= act'(mul_aux[m,n]) (fused activation backward), leading dim ldc
@@ -49,6 +50,7 @@ static inline EpiParams make_epi(const sc_gemm_desc* d) {
   p.c_dtype = d->c_dtype;
   p.C2 = d->C2;
   p.c2_dtype = d->c2_dtype;
+  p.c2_is_act_grad = d->c2_is_act_grad;
   p.accumulate = d->accumulate;
   p.atomic = d->split_k > 1;
   p.mul_aux = d->mul_aux;
@@ -69,7 +71,7 @@ SC_DEVINL void epi_store_scalar(const EpiParams& p, int m, int n, float acc) {
     v += p.rowbias[(long)r * p.ld_rowbias + n];
   }
   long off = (long)m * p.ldc + n;
-  if (p.C2) st_any(p.C2, off, p.c2_dtype, v);
+  if (p.C2) st_any(p.C2, off, p.c2_dtype, p.c2_is_act_grad ? act_grad(v, p.act) : v);
   v = act_fwd(v, p.act);
   if (p.mul_aux) v *= act_grad(ld_any(p.mul_aux, off, p.mul_aux_dtype), p.mul_aux_act);
   if (p.residual) v += ld_any(p.residual, (long)m * p.ldr + n, p.residual_dtype);
@@ -114,7 +116,10 @@ SC_DEVINL void epi_store4(const EpiParams& p, int m, int n, float4 v) {
     v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
   }
   const long off = (long)m * p.ldc + n;
-  if (p.C2) st4(p.C2, off, p.c2_dtype, v);
+  if (p.C2) {
+    if (p.c2_is_act_grad) st4(p.C2, off, p.c2_dtype, make_float4(act_grad(v.x, p.act), act_grad(v.y, p.act), act_grad(v.z, p.act), act_grad(v.w, p.act)));
+    else st4(p.C2, off, p.c2_dtype, v);
+  }
   if (p.act != SC_ACT_NONE) {
     v.x = act_fwd(v.x, p.act); v.y = act_fwd(v.y, p.act); v.z = act_fwd(v.z, p.act); v.w = act_fwd(v.w, p.act);
   }

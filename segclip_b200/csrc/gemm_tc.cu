@@ -170,7 +170,7 @@ int sc_select_epilogue(const sc_gemm_desc* d, int splits) {
     } else if (!aux && !c2 && !resid && d->act == SC_ACT_NONE && out_bf16) {
       ef = bias ? EF_BIAS : 0;
     } else if (bias && c2 && d->c2_dtype == SC_BF16 && out_bf16 && d->act == SC_ACT_QUICKGELU && !resid && !aux) {
-      ef = EF_BIAS | EF_QGELU | EF_C2;
+      ef = EF_BIAS | EF_QGELU | EF_C2 | (d->c2_is_act_grad ? EF_C2_DERIV : 0);
     } else if (bias && resid && d->residual_dtype == SC_F32 && !c2 && !aux && d->act == SC_ACT_NONE && !out_bf16) {
       ef = EF_BIAS | EF_RESID | EF_OUT_F32;
     } else if (bias && resid && d->residual_dtype == SC_BF16 && !c2 && !aux && d->act == SC_ACT_NONE && out_bf16) {
@@ -178,8 +178,11 @@ int sc_select_epilogue(const sc_gemm_desc* d, int splits) {
     } else if (aux && d->mul_aux_dtype == SC_BF16 && d->mul_aux_act == SC_ACT_QUICKGELU && !bias && !resid && !c2 &&
                d->act == SC_ACT_NONE && out_bf16) {
       ef = EF_MULAUX_QGELU;
+    } else if (aux && d->mul_aux_dtype == SC_BF16 && d->mul_aux_act == SC_ACT_DERIV && !bias && !resid && !c2 &&
+               d->act == SC_ACT_NONE && out_bf16) {
+      ef = EF_MULAUX_DERIV;
     } else if (bias && c2 && d->c2_dtype == SC_BF16 && out_bf16 && d->act == SC_ACT_GELU_ERF && !resid && !aux) {
-      ef = EF_BIAS | EF_GELU | EF_C2;
+      ef = EF_BIAS | EF_GELU | EF_C2 | (d->c2_is_act_grad ? EF_C2_DERIV : 0);
     } else if (aux && d->mul_aux_dtype == SC_BF16 && d->mul_aux_act == SC_ACT_GELU_ERF && !bias && !resid && !c2 &&
                d->act == SC_ACT_NONE && out_bf16) {
       ef = EF_MULAUX_GELU;
@@ -463,6 +466,8 @@ static int sc_gemm_tc_impl(const sc_gemm_desc* d, cudaStream_t st) {
     if (ef == EF_BIAS) SC_L(BN_, false, false, EF_BIAS)                                      \
     if (ef == 0) SC_L(BN_, false, false, 0)                                                  \
     if (ef == (EF_BIAS | EF_QGELU | EF_C2)) SC_L(BN_, false, false, EF_BIAS | EF_QGELU | EF_C2) \
+    if (ef == (EF_BIAS | EF_QGELU | EF_C2 | EF_C2_DERIV)) SC_L(BN_, false, false, EF_BIAS | EF_QGELU | EF_C2 | EF_C2_DERIV) \
+    if (ef == (EF_BIAS | EF_GELU | EF_C2 | EF_C2_DERIV)) SC_L(BN_, false, false, EF_BIAS | EF_GELU | EF_C2 | EF_C2_DERIV) \
     if (ef == (EF_BIAS | EF_RESID | EF_OUT_F32)) SC_L(BN_, false, false, EF_BIAS | EF_RESID | EF_OUT_F32) \
     if (ef == (EF_BIAS | EF_GELU | EF_C2)) SC_L(BN_, false, false, EF_BIAS | EF_GELU | EF_C2)  \
     if (ef == EF_OUT_F32) SC_L(BN_, false, false, EF_OUT_F32)                                \
@@ -472,6 +477,7 @@ static int sc_gemm_tc_impl(const sc_gemm_desc* d, cudaStream_t st) {
     if (ef == 0) SC_L(BN_, false, true, 0)                                                   \
     if (ef == EF_MULAUX_QGELU) SC_L(BN_, false, true, EF_MULAUX_QGELU)                       \
     if (ef == EF_MULAUX_GELU) SC_L(BN_, false, true, EF_MULAUX_GELU)                         \
+    if (ef == EF_MULAUX_DERIV) SC_L(BN_, false, true, EF_MULAUX_DERIV)                       \
     if (ef == EF_OUT_F32) SC_L(BN_, false, true, EF_OUT_F32)                                 \
     if (ef == (EF_OUT_F32 | EF_ACCUM)) SC_L(BN_, false, true, EF_OUT_F32 | EF_ACCUM)         \
     SC_L(BN_, false, true, EF_GENERIC)                                                       \

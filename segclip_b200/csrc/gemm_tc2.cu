@@ -365,6 +365,8 @@ int sc_gemm_tc2(const sc_gemm_desc* d, cudaStream_t st) {
     if (ef == EF_BIAS) SC_L2(false, false, EF_BIAS)
     if (ef == 0) SC_L2(false, false, 0)
     if (ef == (EF_BIAS | EF_QGELU | EF_C2)) SC_L2(false, false, EF_BIAS | EF_QGELU | EF_C2)
+    if (ef == (EF_BIAS | EF_QGELU | EF_C2 | EF_C2_DERIV)) SC_L2(false, false, EF_BIAS | EF_QGELU | EF_C2 | EF_C2_DERIV)
+    if (ef == (EF_BIAS | EF_GELU | EF_C2 | EF_C2_DERIV)) SC_L2(false, false, EF_BIAS | EF_GELU | EF_C2 | EF_C2_DERIV)
     if (ef == (EF_BIAS | EF_RESID | EF_OUT_F32)) SC_L2(false, false, EF_BIAS | EF_RESID | EF_OUT_F32)
     if (ef == (EF_BIAS | EF_RESID_BF)) SC_L2(false, false, EF_BIAS | EF_RESID_BF)
     if (ef == (EF_BIAS | EF_GELU | EF_C2)) SC_L2(false, false, EF_BIAS | EF_GELU | EF_C2)
@@ -379,6 +381,7 @@ int sc_gemm_tc2(const sc_gemm_desc* d, cudaStream_t st) {
     if (ef == 0) SC_L2(false, true, 0)
     if (ef == EF_MULAUX_QGELU) SC_L2(false, true, EF_MULAUX_QGELU)
     if (ef == EF_MULAUX_GELU) SC_L2(false, true, EF_MULAUX_GELU)
+    if (ef == EF_MULAUX_DERIV) SC_L2(false, true, EF_MULAUX_DERIV)
     if (ef == EF_OUT_F32) SC_L2(false, true, EF_OUT_F32)
     if (ef == (EF_OUT_F32 | EF_ACCUM)) SC_L2(false, true, EF_OUT_F32 | EF_ACCUM)
     SC_L2(false, true, EF_GENERIC)

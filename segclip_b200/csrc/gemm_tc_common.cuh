@@ -149,6 +149,8 @@ enum : int {
   EF_ACCUM = 512,       // C += result (fp32 read-modify-write, single split; old C prefetched like a residual)
   EF_RESID_BF = 1024,   // + residual (bf16), bf16 output: the bf16 residual stream (2-CTA kernel: residual tile through the TMA)
   EF_ROWDOT = 2048,     // plain bf16 output + per-head row dots with a second bf16 tile (attention delta from the out_proj dgrad)
+  EF_C2_DERIV = 4096,   // with EF_C2: the second output is act'(v), not v (the sigmoid / erf is at hand in the forward epilogue)
+  EF_MULAUX_DERIV = 8192, // * aux, aux = act'(pre-activation) stored by the forward (3 instructions per element instead of ~10)
   EF_GENERIC = 1 << 20
 };
 
@@ -159,6 +161,17 @@ SC_DEVINL float tanh_fast(float x) {
 }
 // x*sigmoid(1.702x) with one MUFU: sigmoid(y) = 0.5 + 0.5 tanh(y/2)
 SC_DEVINL float qgelu_fast(float x) { return x * fmaf(0.5f, tanh_fast(0.851f * x), 0.5f); }
+// y = QuickGELU(x), g = QuickGELU'(x) from ONE tanh: g = s (1 + 1.702 x (1 - s)) = s + 1.702 y (1 - s)
+SC_DEVINL void qgelu_both(float x, float& y, float& g) {
+  const float s = fmaf(0.5f, tanh_fast(0.851f * x), 0.5f);
+  y = x * s;
+  g = fmaf(1.702f * y, 1.0f - s, s);
+}
+template <int EF>
+SC_DEVINL void act_both(float x, float& y, float& g) {
+  if constexpr ((EF & EF_QGELU) != 0) qgelu_both(x, y, g);
+  else { y = act_fwd(x, SC_ACT_GELU_ERF); g = act_grad(x, SC_ACT_GELU_ERF); }
+}
 SC_DEVINL float qgelu_grad_fast(float x) {
   const float s = fmaf(0.5f, tanh_fast(0.851f * x), 0.5f);
   return s * fmaf(1.702f * x, 1.0f - s, 1.0f);
@@ -240,7 +253,7 @@ SC_DEVINL float2 unpack2_bf16(uint32_t u) { return __bfloat1622float2(*(const __
 template <int EF>
 struct EpiKind {
   static constexpr bool bf16_path = (EF != EF_GENERIC) && (EF & (EF_OUT_F32 | EF_ATOMIC | EF_RESID)) == 0;
-  static constexpr bool aux = (EF != EF_GENERIC) && (EF & (EF_MULAUX_QGELU | EF_MULAUX_GELU)) != 0;
+  static constexpr bool aux = (EF != EF_GENERIC) && (EF & (EF_MULAUX_QGELU | EF_MULAUX_GELU | EF_MULAUX_DERIV)) != 0;
 };
 
 template <int EF>
@@ -294,6 +307,20 @@ SC_DEVINL void epi_finish(const EpiParams& ep, float (&v)[32], uint32_t stage, i
     const uint32_t rowaddr = stage + lane * 64;
     const int sw = (lane >> 1) & 3;
     __syncwarp();
+    if constexpr ((EF & EF_C2) != 0 && (EF & EF_C2_DERIV) != 0) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        uint32_t gp[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          float g0, g1;
+          act_both<EF>(v[8 * j + 2 * k], v[8 * j + 2 * k], g0);
+          act_both<EF>(v[8 * j + 2 * k + 1], v[8 * j + 2 * k + 1], g1);
+          gp[k] = pack2_bf16(g0, g1);
+        }
+        sts128b(rowaddr + ((j ^ sw) << 4), make_uint4(gp[0], gp[1], gp[2], gp[3]));
+      }
+    } else {
     if constexpr ((EF & EF_C2) != 0) {
 #pragma unroll
       for (int j = 0; j < 4; ++j)
@@ -307,6 +334,7 @@ SC_DEVINL void epi_finish(const EpiParams& ep, float (&v)[32], uint32_t stage, i
     if constexpr ((EF & EF_GELU) != 0) {
 #pragma unroll
       for (int j = 0; j < 32; ++j) v[j] = act_fwd(v[j], SC_ACT_GELU_ERF);
+    }
     }
     constexpr uint32_t out_tile = (EF & EF_C2) != 0 ? 2048u : 0u;
 #pragma unroll
@@ -335,7 +363,8 @@ SC_DEVINL void epi_finish(const EpiParams& ep, float (&v)[32], uint32_t stage, i
           for (int k = 0; k < 4; ++k) {
             const float2 x = unpack2_bf16(uw[k]), g = unpack2_bf16(aw[k]);
             float g0, g1;
-            if constexpr ((EF & EF_MULAUX_QGELU) != 0) { g0 = qgelu_grad_fast(g.x); g1 = qgelu_grad_fast(g.y); }
+            if constexpr ((EF & EF_MULAUX_DERIV) != 0) { g0 = g.x; g1 = g.y; }
+            else if constexpr ((EF & EF_MULAUX_QGELU) != 0) { g0 = qgelu_grad_fast(g.x); g1 = qgelu_grad_fast(g.y); }
             else { g0 = act_grad(g.x, SC_ACT_GELU_ERF); g1 = act_grad(g.y, SC_ACT_GELU_ERF); }
             uw[k] = pack2_bf16(x.x * g0, x.y * g1);
           }
@@ -427,7 +456,7 @@ struct EpiTma {
 // tile start (while the tile's main loop still runs) on one mbarrier each.
 template <int EF>
 struct EpiAuxTma {
-  static constexpr bool value = (EF != EF_GENERIC) && (EF & (EF_RESID_BF | EF_MULAUX_QGELU | EF_MULAUX_GELU | EF_ROWDOT)) != 0 &&
+  static constexpr bool value = (EF != EF_GENERIC) && (EF & (EF_RESID_BF | EF_MULAUX_QGELU | EF_MULAUX_GELU | EF_MULAUX_DERIV | EF_ROWDOT)) != 0 &&
                                 (EF & (EF_OUT_F32 | EF_ATOMIC | EF_RESID | EF_C2)) == 0;
 };
 
@@ -459,6 +488,7 @@ SC_DEVINL void epi_finish_aux_tma(const EpiParams& ep, float (&v)[32], uint32_t 
       if constexpr ((EF & EF_RESID_BF) != 0) { o0 += x.x; o1 += x.y; }
       if constexpr ((EF & EF_MULAUX_QGELU) != 0) { o0 *= qgelu_grad_fast(x.x); o1 *= qgelu_grad_fast(x.y); }
       if constexpr ((EF & EF_MULAUX_GELU) != 0) { o0 *= act_grad(x.x, SC_ACT_GELU_ERF); o1 *= act_grad(x.y, SC_ACT_GELU_ERF); }
+      if constexpr ((EF & EF_MULAUX_DERIV) != 0) { o0 *= x.x; o1 *= x.y; }
       if constexpr ((EF & EF_ROWDOT) != 0) dotacc = fmaf(o0, x.x, fmaf(o1, x.y, dotacc));
       ow[k] = pack2_bf16(o0, o1);
     }
@@ -569,6 +599,21 @@ SC_DEVINL void epi_finish_tma(const EpiParams& ep, float (&v)[32], uint32_t stag
   }
   const int sw = (lane >> 1) & 3;
   __syncwarp();
+  if constexpr (two && (EF & EF_C2_DERIV) != 0) {
+    // second output = act'(v): activation and derivative from the same sigmoid / erf
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      uint32_t gp[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        float g0, g1;
+        act_both<EF>(v[8 * j + 2 * k], v[8 * j + 2 * k], g0);
+        act_both<EF>(v[8 * j + 2 * k + 1], v[8 * j + 2 * k + 1], g1);
+        gp[k] = pack2_bf16(g0, g1);
+      }
+      sts128b(buf_c2 + lane * 64 + ((j ^ sw) << 4), make_uint4(gp[0], gp[1], gp[2], gp[3]));
+    }
+  } else {
   if constexpr (two) {
 #pragma unroll
     for (int j = 0; j < 4; ++j)
@@ -582,6 +627,7 @@ SC_DEVINL void epi_finish_tma(const EpiParams& ep, float (&v)[32], uint32_t stag
   if constexpr ((EF & EF_GELU) != 0) {
 #pragma unroll
     for (int j = 0; j < 32; ++j) v[j] = act_fwd(v[j], SC_ACT_GELU_ERF);
+  }
   }
 #pragma unroll
   for (int j = 0; j < 4; ++j)

@@ -362,14 +362,17 @@ class Engine:
             h2 = buf(tag + ".ln2", (M, D), T)
             st2 = ln_fwd(x_mid, pre + nm["ln2"], h2, tag + ".ln2", eps)
             hpre, hact = buf(tag + ".fc_pre", (M, Dh), T), buf(tag + ".fc_act", (M, Dh), T)
-            pl.f(ops.gemm_op(h2, self.W(pre + nm["w1"]), hact, bias=self.P(pre + nm["b1"]), act=act, C2=hpre))
+            # bf16 mode: the forward epilogue stores act'(pre-activation) instead of the pre-activation (it has the sigmoid /
+            # erf at hand); the fused activation backward in the c_proj dgrad epilogue is then a plain multiply
+            deriv = is_bf16 and not os.environ.get("SC_NO_FUSE_ACT") and not os.environ.get("SC_NO_ACT_DERIV")
+            pl.f(ops.gemm_op(h2, self.W(pre + nm["w1"]), hact, bias=self.P(pre + nm["b1"]), act=act, C2=hpre, c2_is_act_grad=deriv))
             pl.f(ops.gemm_op(hact, self.W(pre + nm["w2"]), x_out, bias=self.P(pre + nm["b2"]), residual=x_mid))
             d_a, d_ln = sbuf("d_a", (M, Dh), T), sbuf("d_ln", (M, D), T)
             if os.environ.get("SC_NO_FUSE_ACT"):
                 grp = linear_bwd(dxT, hact, pre + nm["w2"], pre + nm["b2"], dx=d_a)
                 grp.append(ops.act_bwd_op(d_a, hpre, d_a, act))
             else:
-                grp = linear_bwd(dxT, hact, pre + nm["w2"], pre + nm["b2"], dx=d_a, mul_aux=hpre, mul_act=act,  # fused act'()
+                grp = linear_bwd(dxT, hact, pre + nm["w2"], pre + nm["b2"], dx=d_a, mul_aux=hpre, mul_act=ops.ACT_DERIV if deriv else act,  # fused act'()
                                  dx_colsum=self.grads[pre + nm["b1"]] if is_bf16 else None)                    # + c_fc bias grad
             fused_b1 = is_bf16 and not os.environ.get("SC_NO_FUSE_ACT")
             grp += linear_bwd(d_a, h2, pre + nm["w1"], None if fused_b1 else pre + nm["b1"], dx=d_ln)

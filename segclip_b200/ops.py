@@ -10,6 +10,8 @@ import torch
 from . import _lib as L
 from ._lib import ACT_GELU_ERF, ACT_NONE, ACT_QUICKGELU, BF16, F32  # noqa: F401
 
+ACT_DERIV = 3        # mul_aux_act: mul_aux already holds act'(pre-activation) (forward gemm with c2_is_act_grad)
+
 
 class Op:
     __slots__ = ("fn", "args", "keep", "name")
@@ -36,7 +38,7 @@ def _p(t):
 
 def gemm_desc(A, B, C_, *, trans_a=False, trans_b=False, bias=None, rowbias=None, rowbias_idx=None, rowbias_mod=0,
               act=ACT_NONE, residual=None, C2=None, accumulate=False, split_k=0, alpha=1.0, force_simt=False,
-              mul_aux=None, mul_aux_act=ACT_NONE, colsum_out=None, dot_aux=None, dot_out=None, dot_L=0):
+              mul_aux=None, mul_aux_act=ACT_NONE, colsum_out=None, dot_aux=None, dot_out=None, dot_L=0, c2_is_act_grad=False):
     """sc_gemm descriptor for C = epi(A B^T); see include/segclip_b200.h."""
     for t in (A, B, C_):
         _chk2d(t)
@@ -72,6 +74,7 @@ def gemm_desc(A, B, C_, *, trans_a=False, trans_b=False, bias=None, rowbias=None
         _chk2d(C2)
         assert C2.shape == C_.shape and C2.stride(0) == C_.stride(0)
         d.C2, d.c2_dtype = C2.data_ptr(), L.dt(C2)
+        d.c2_is_act_grad = int(c2_is_act_grad)
     if accumulate:
         assert C_.dtype == torch.float32
     d.accumulate, d.split_k, d.force_simt = int(accumulate), split_k, int(force_simt)

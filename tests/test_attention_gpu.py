@@ -59,7 +59,7 @@ def _run(B, H, L, hd, dtype, causal=False, force_generic=False, seed=0, ramp=0.0
 
 @pytest.mark.parametrize("B,H,L,hd,causal", [(3, 12, 196, 64, False), (2, 8, 77, 64, True), (2, 8, 197, 48, False),
                                              (2, 12, 48, 64, False), (1, 2, 16, 32, False), (3, 2, 16, 64, False), (3, 1, 16, 64, True), (2, 4, 130, 64, True),
-                                             (1, 2, 577, 64, False)])
+                                             (1, 2, 577, 64, False), (5, 12, 8, 64, False), (3, 4, 5, 64, False)])
 def test_tensor_core_attention(B, H, L, hd, causal):
     _run(B, H, L, hd, torch.bfloat16, causal)
 

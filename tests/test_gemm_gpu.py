@@ -259,3 +259,35 @@ def test_dgrad_with_fused_attention_delta(B, L):
     assert float((dO.float() - ref).abs().max() / ref.abs().max()) < 1e-2
     want = (ref * O.float()).view(B, L, H, 64).sum(-1).permute(0, 2, 1)
     assert float((delta - want).abs().max()) < 2e-2 * float(want.abs().max())
+
+
+@pytest.mark.parametrize("M", [1576, 392])
+@pytest.mark.parametrize("act", [1, 2])
+def test_forward_stores_activation_derivative_and_backward_multiplies(M, act):
+    """c_fc forward with C2 := act'(pre-activation) (QuickGELU: from the same sigmoid as the activation) and the c_proj dgrad
+    that multiplies with it (mul_aux_act = ACT_DERIV) -- against autograd; 2-CTA (M >= 512) and 1-CTA kernels."""
+    from segclip_b200 import ops
+    torch.manual_seed(M + act)
+    N, K = 3072, 768
+    x = torch.randn(M, K, device="cuda").bfloat16()
+    W1 = (torch.randn(N, K, device="cuda") * 0.05).bfloat16()
+    b1 = torch.randn(N, device="cuda") * 0.1
+    hact = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
+    hder = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
+    ops.gemm(x, W1, hact, bias=b1, act=act, C2=hder, c2_is_act_grad=True)
+    pre = (x.float() @ W1.float().t() + b1).requires_grad_(True)
+    y = pre * torch.sigmoid(1.702 * pre) if act == 1 else torch.nn.functional.gelu(pre)
+    y.backward(torch.ones_like(y))
+    assert float((hact.float() - y.detach()).abs().max() / y.abs().max()) < 1e-2
+    assert float((hder.float() - pre.grad).abs().max()) < 1.2e-2          # derivative values are O(1)
+    # backward: d_a = (dY W2) * stored derivative (+ fused column sums = c_fc bias gradient)
+    dy = torch.randn(M, K, device="cuda").bfloat16()
+    W2 = (torch.randn(K, N, device="cuda") * 0.05).bfloat16()
+    d_a = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
+    cs = torch.zeros(N, device="cuda")
+    ops.gemm(dy, W2, d_a, trans_b=True, mul_aux=hder, mul_aux_act=ops.ACT_DERIV, colsum_out=cs)
+    torch.cuda.synchronize()
+    want = (dy.float() @ W2.float()) * hder.float()
+    assert float((d_a.float() - want).abs().max() / want.abs().max()) < 1e-2
+    ref = d_a.float().sum(0)
+    assert float((cs - ref).abs().max()) < 2e-3 * (1 + float(ref.abs().max()))

@@ -24,6 +24,9 @@ SHAPES = [  # name, M, N, K, ta, tb, kwargs
     ("text c_proj fwd", 19712, 512, 2048, False, False, dict(bias=True, residual=True, out=torch.float32)),
     ("text out_proj fwd", 19712, 512, 512, False, False, dict(bias=True, residual=True, out=torch.float32)),
     ("c_proj dgrad*+cs", 50176, 3072, 768, False, True, dict(out=torch.bfloat16, aux=True, colsum=True)),
+    ("c_fc fwd (deriv)", 50176, 3072, 768, False, False, dict(bias=True, act=1, c2=True, out=torch.bfloat16, deriv=True)),
+    ("c_proj dgrad' +cs", 50176, 3072, 768, False, True, dict(out=torch.bfloat16, aux=True, colsum=True, deriv=True)),
+    ("text c_proj dgrad'", 19712, 2048, 512, False, True, dict(out=torch.bfloat16, aux=True, colsum=True, deriv=True)),
     ("plain 8192^3", 8192, 8192, 8192, False, False, dict(out=torch.bfloat16)),
 ]
 
@@ -43,7 +46,8 @@ def main():
         aux = torch.randn(M, N, device=dev).bfloat16() if kw.get("aux") else None
         cs = torch.zeros(N, device=dev) if kw.get("colsum") else None
         op = ops.gemm_op(A, B, C, trans_a=ta, trans_b=tb, bias=bias, residual=res, act=kw.get("act", 0), C2=C2,
-                         mul_aux=aux, mul_aux_act=1 if aux is not None else 0, colsum_out=cs,
+                         mul_aux=aux, mul_aux_act=(3 if kw.get("deriv") else 1) if aux is not None else 0, colsum_out=cs,
+                         c2_is_act_grad=bool(kw.get("deriv")) and C2 is not None,
                          accumulate=kw.get("acc", False), split_k=-1 if kw.get("acc") else 0)
         for _ in range(3):
             op()
