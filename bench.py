@@ -103,35 +103,63 @@ def synthetic_batch(cfg, B, seed, rank, heads):
     return dict(input_ids=ids, attention_mask=(ids != 0).long(), image=image, image_seg=seg)
 
 
-def run_reference(args):
-    """CPU arm: oracle port of the reference's PyTorch path, fp32, all host threads."""
-    rank = int(os.environ.get("RANK", "0"))
-    if rank != 0:
-        return
+def _cpu_arm(args, steps, warmup):
+    """One CPU measurement of the hot path on all host cores, fp32, batch args.cpu_batch of the same synthetic workload:
+    the UNMODIFIED reference's own nn.Module (oracle/_ref, kind "reference") when it is available, else the oracle port
+    (kind "port").  Returns (ms per step list, kind)."""
+    from oracle import ref_harness as rh
     from oracle import segclip_oracle as so
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
     cfg = model_config(args)
     Bc = args.cpu_batch
-    params = so.init_params(cfg, seed=0)
-    frozen = ("vis_mae_decoder.decoder_pos_embed",)
     batch, noise = so.make_batch(cfg, Bc, seed=0)
+    kind = "port"
+    model = None
+    if rh.reference_available() and not os.environ.get("SEGCLIP_CPU_ARM_PORT"):
+        try:
+            os.environ["MASTER_ADDR"] = "127.0.0.1"
+            os.environ["MASTER_PORT"] = str(29800 + os.getpid() % 150)      # not torchrun's rendezvous port
+            if torch.distributed.is_available() and torch.distributed.is_initialized():
+                raise RuntimeError("process group already initialised")
+            torch.manual_seed(0)
+            model = rh.build_reference_model(cfg)
+            kind = "reference"
+        except Exception as e:          # fall back to the port, say so
+            sys.stderr.write("reference arm unavailable (%s: %s); timing the oracle port\n" % (type(e).__name__, e))
+            model = None
+    params = so.init_params(cfg, seed=0) if model is None else None
+    frozen = ("vis_mae_decoder.decoder_pos_embed",)
     times = []
-    for i in range(args.warmup + args.steps):
+    for i in range(warmup + steps):
         t0 = time.perf_counter()
-        so.loss_and_grads(params, batch, noise, cfg, "torch18_flat", frozen=frozen)
+        if model is not None:
+            rh.run_reference(model, batch, noise, cfg["use_mae"])
+        else:
+            so.loss_and_grads(params, batch, noise, cfg, "torch18_flat", frozen=frozen)
         dt = time.perf_counter() - t0
-        if i >= args.warmup:
+        if i >= warmup:
             times.append(dt)
+    return times, kind, cores
+
+
+def run_reference(args):
+    """CPU arm: the reference's own PyTorch path (or the oracle port when the reference copy is absent), fp32, all host threads."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    Bc = args.cpu_batch
+    times, kind, cores = _cpu_arm(args, args.steps, args.warmup)
     ms = 1e3 * sum(times) / len(times)
     v = Bc / (ms / 1e3)
-    sample = "batch %d of the same synthetic workload, fp32, %d steps after %d warm-up" % (Bc, args.steps, args.warmup)
+    what = "the unmodified reference nn.Module (oracle/_ref + 6 import shims)" if kind == "reference" else "oracle port"
+    sample = "%s, batch %d of the same synthetic workload, fp32, %d steps after %d warm-up" % (what, Bc, args.steps, args.warmup)
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": v, "unit": "pairs/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": workload_name(args), "cpu_batch": Bc},
-        "cpu_baseline": {"value": v, "unit": "pairs/s", "cores": cores, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": v, "unit": "pairs/s", "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": v, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
 
 
@@ -307,23 +335,12 @@ def gemm_traffic(args):
 
 
 def cpu_baseline(args):
-    """The only leg of the own arm that touches oracle/: the CPU port timed beside the GPU number."""
-    from oracle import segclip_oracle as so
-    cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
-    cfg = model_config(args)
-    Bc = args.cpu_batch
-    params = so.init_params(cfg, seed=0)
-    batch, noise = so.make_batch(cfg, Bc, seed=0)
-    best = None
-    for i in range(3):
-        t0 = time.perf_counter()
-        so.loss_and_grads(params, batch, noise, cfg, "torch18_flat", frozen=("vis_mae_decoder.decoder_pos_embed",))
-        dt = time.perf_counter() - t0
-        if i > 0:
-            best = dt if best is None else min(best, dt)
-    return {"value": Bc / best, "unit": "pairs/s", "cores": cores, "kind": "port",
-            "sample": "oracle port (fp32 PyTorch CPU), batch %d, best of 2 after 1 warm-up" % Bc}
+    """The only leg of the own arm that touches oracle/: the CPU path timed beside the GPU number (bounded sample)."""
+    times, kind, cores = _cpu_arm(args, 2, 1)
+    best = min(times)
+    what = "unmodified reference nn.Module (oracle/_ref)" if kind == "reference" else "oracle port"
+    return {"value": args.cpu_batch / best, "unit": "pairs/s", "cores": cores, "kind": kind,
+            "sample": "%s (fp32 PyTorch CPU), batch %d, best of 2 after 1 warm-up" % (what, args.cpu_batch)}
 
 
 if __name__ == "__main__":

@@ -1,4 +1,4 @@
-"""TEST INFRASTRUCTURE ONLY -- imports the UNMODIFIED reference from /root/reference.
+"""TEST INFRASTRUCTURE ONLY -- imports the UNMODIFIED reference from /root/reference (or its untouched copy oracle/_ref).
 
 Used (a) by ``tests/golden/make_golden.py`` to generate the committed golden
 vectors and (b) by ``tests/test_oracle_vs_reference.py`` (skipped when the
@@ -29,7 +29,17 @@ import torch
 import torch.distributed as dist
 import torch.nn.functional as F
 
-REF_ROOT = os.environ.get("SEGCLIP_REFERENCE", "/root/reference")
+def _find_reference():
+    """The reference tree: $SEGCLIP_REFERENCE, the container's /root/reference, or the untouched copy that
+    oracle/make_ref.py placed under oracle/_ref (the only one that exists on the GPU box)."""
+    cands = [os.environ.get("SEGCLIP_REFERENCE"), "/root/reference", os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref")]
+    for c in cands:
+        if c and os.path.isfile(os.path.join(c, "modules", "modeling.py")):
+            return c
+    return "/root/reference"
+
+
+REF_ROOT = _find_reference()
 
 
 def reference_available() -> bool:

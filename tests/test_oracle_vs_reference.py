@@ -81,3 +81,19 @@ def test_eval_mode_other_resolutions_match_reference(hw):
     for a, b in ((x, ox), (hid, ohid), (mid["hidden"], omid["hidden"]),
                  (mid["attns"][0]["soft_attn"], omid["attns"][0]["soft_attn"])):
         assert a.shape == b.shape and float((a - b).abs().max()) < 1e-5
+
+
+def test_reference_copy_for_the_gpu_box_is_untouched(tmp_path):
+    """oracle/make_ref.py (run by __graft_entry__.build()) places an UNMODIFIED copy of the reference's Python modules under
+    oracle/_ref for bench.py's reference arm on the GPU box: byte-identical files, git-ignored."""
+    import filecmp
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    subprocess.run([sys.executable, os.path.join(root, "oracle", "make_ref.py")], check=True, capture_output=True)
+    ref = "/root/reference"
+    for f in [os.path.join("modules", x) for x in os.listdir(os.path.join(ref, "modules")) if x.endswith(".py")] + ["util.py"]:
+        assert filecmp.cmp(os.path.join(ref, f), os.path.join(root, "oracle", "_ref", f), shallow=False), f
+    ignored = subprocess.run(["git", "check-ignore", "oracle/_ref/util.py"], cwd=root, capture_output=True, text=True)
+    assert ignored.returncode == 0, "oracle/_ref must stay out of the repository history"
