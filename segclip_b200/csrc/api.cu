@@ -1,5 +1,6 @@
 // Library-level plumbing: error text, launch counter, sc_gemm dispatch.
 #include <stdarg.h>
+#include <stdlib.h>
 
 #include <atomic>
 
@@ -33,6 +34,14 @@ int sc_num_sms() {
     cache[dev & 63].store(n, std::memory_order_relaxed);
   }
   return n;
+}
+
+bool sc_pdl_enabled() {
+  static const bool on = []() {
+    const char* e = getenv("SC_PDL");
+    return !(e && e[0] == '0');
+  }();
+  return on;
 }
 
 // Entry points may be called from a thread that has not touched the CUDA runtime yet (autograd's

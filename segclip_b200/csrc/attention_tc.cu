@@ -197,16 +197,21 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   }
   if (warp == NSOFT) {
     __syncwarp();
-    issue_group(blockIdx.x, 0, 0);    // flies while TMEM is allocated
-    if (ntile > 1) issue_group(blockIdx.x, 1, 1);
-    else if ((int)(blockIdx.x + gridDim.x) < total) issue_group(blockIdx.x + gridDim.x, 0, 1);
+    // dependent launch (common.cuh): barriers and TMEM under the previous kernel's tail, global reads after pdl_wait
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    pdl_wait();
+    issue_group(blockIdx.x, 0, 0);
+    if (ntile > 1) issue_group(blockIdx.x, 1, 1);
+    else if ((int)(blockIdx.x + gridDim.x) < total) issue_group(blockIdx.x + gridDim.x, 0, 1);
+  } else {
+    pdl_wait();
   }
   tcgen05_fence_before();
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem = *tmem_slot;
+  pdl_launch_dependents();      // only now: a successor CTA sharing this SM must find this CTA's TMEM already allocated
   const float c = a.scale * LOG2E_F;
 
   if (warp == NSOFT) {
@@ -650,15 +655,19 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   }
   if (warp == F_NSOFT) {
     __syncwarp();
-    issue_qk(blockIdx.x);
-    issue_v(blockIdx.x);
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(F_TM_COLS) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    pdl_wait();                      // (common.cuh) everything above ran under the previous kernel's tail
+    issue_qk(blockIdx.x);
+    issue_v(blockIdx.x);
+  } else {
+    pdl_wait();
   }
   tcgen05_fence_before();
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem = *tmem_slot;
+  pdl_launch_dependents();      // only now: a successor CTA sharing this SM must find this CTA's TMEM already allocated
 
   if (warp == F_NSOFT) {
     {   // warp-uniform control flow; single-lane instructions are elected inside the *_e wrappers
@@ -1055,11 +1064,11 @@ int sc_attention_bwd_tc(const sc_attn_bwd_desc* g, float* delta, cudaStream_t st
   if (a->causal) {
     static sc_device_once once;
     if (once.first()) { SC_CUDA(cudaFuncSetAttribute(attn_bwd_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL)); once.done(); }
-    attn_bwd_tc_kernel<true><<<grid, TC_THREADS, SMEM_TOTAL, st>>>(tq, tk, tv, tdo, gq, gk, gv, *g, delta);
+    SC_CUDA(sc_launch_pdl(attn_bwd_tc_kernel<true>, grid, dim3(TC_THREADS), SMEM_TOTAL, st, tq, tk, tv, tdo, gq, gk, gv, *g, delta));
   } else {
     static sc_device_once once;
     if (once.first()) { SC_CUDA(cudaFuncSetAttribute(attn_bwd_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL)); once.done(); }
-    attn_bwd_tc_kernel<false><<<grid, TC_THREADS, SMEM_TOTAL, st>>>(tq, tk, tv, tdo, gq, gk, gv, *g, delta);
+    SC_CUDA(sc_launch_pdl(attn_bwd_tc_kernel<false>, grid, dim3(TC_THREADS), SMEM_TOTAL, st, tq, tk, tv, tdo, gq, gk, gv, *g, delta));
   }
   SC_LAUNCH_CHECK();
   return SC_OK;
@@ -1083,11 +1092,11 @@ int sc_attention_fwd_tc(const sc_attn_desc* a, cudaStream_t st) {
   if (a->causal) {
     static sc_device_once once;
     if (once.first()) { SC_CUDA(cudaFuncSetAttribute(attn_fwd_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, F_SMEM_TOTAL)); once.done(); }
-    attn_fwd_tc_kernel<true><<<grid, F_THREADS, F_SMEM_TOTAL, st>>>(tq, tk, tv, to, *a, online);
+    SC_CUDA(sc_launch_pdl(attn_fwd_tc_kernel<true>, grid, dim3(F_THREADS), F_SMEM_TOTAL, st, tq, tk, tv, to, *a, online));
   } else {
     static sc_device_once once;
     if (once.first()) { SC_CUDA(cudaFuncSetAttribute(attn_fwd_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, F_SMEM_TOTAL)); once.done(); }
-    attn_fwd_tc_kernel<false><<<grid, F_THREADS, F_SMEM_TOTAL, st>>>(tq, tk, tv, to, *a, online);
+    SC_CUDA(sc_launch_pdl(attn_fwd_tc_kernel<false>, grid, dim3(F_THREADS), F_SMEM_TOTAL, st, tq, tk, tv, to, *a, online));
   }
   SC_LAUNCH_CHECK();
   return SC_OK;

@@ -40,6 +40,33 @@ void sc_set_error(const char* fmt, ...);
 
 int sc_num_sms();   // SM count of the CURRENT device (cached per device)
 
+// ---- programmatic dependent launch ------------------------------------------------------------------
+// A step is ~600 back-to-back launches on one stream, most of them persistent kernels whose CTAs all retire within a few
+// microseconds of each other.  Launched with cudaLaunchAttributeProgrammaticStreamSerialization a kernel's CTAs are
+// scheduled onto an SM as soon as the previous kernel's CTAs have left it: launch latency and the prologue (mbarrier
+// init, TMEM allocation, tensor-map prefetch) run under the previous kernel's tail.  Every kernel launched this way
+// executes pdl_launch_dependents() first (lets ITS successor in) and pdl_wait() -- which returns once the previous
+// grid has completed and its writes are visible -- before its first global-memory access.  SC_PDL=0 = plain launches.
+bool sc_pdl_enabled();
+SC_DEVINL void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+SC_DEVINL void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+template <typename... KArgs, typename... Args>
+static inline cudaError_t sc_launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                                        Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = sc_pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+
 // Once-per-(call site, device) latch for cudaFuncSetAttribute: the attribute is per device and entry points are called
 // from several host threads (autograd runs backward on its own thread), so the latch is an atomic per-device bit mask.
 // Two threads racing on the first call both set the (idempotent) attribute.

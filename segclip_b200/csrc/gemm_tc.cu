@@ -246,6 +246,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_launch_dependents();      // after the TMEM allocation: a successor CTA sharing this SM can never starve this one
+  pdl_wait();                   // prologue above overlaps the previous kernel's tail (common.cuh)
 
   const int num_items = tiles_m * tiles_n * splits;
 
@@ -379,8 +381,8 @@ int launch(const sc_gemm_desc* d, const CUtensorMap& ta, const CUtensorMap& tb, 
   EpiParams ep = make_epi(&dd);
   const int items = tiles_m * tiles_n * splits;
   const int grid = items < sc_num_sms() ? items : sc_num_sms();
-  kern<<<grid, NUM_THREADS, Cfg::SMEM_BYTES, st>>>(ta, tb, tiles_m, tiles_n, splits, kb_total, kb_per, ep);
-  SC_LAUNCH_CHECK();
+  SC_CUDA(sc_launch_pdl(kern, dim3(grid), dim3(NUM_THREADS), Cfg::SMEM_BYTES, st, ta, tb, tiles_m, tiles_n, splits, kb_total,
+                        kb_per, ep));
   return SC_OK;
 }
 

@@ -125,6 +125,8 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const int num_items = tiles_m * tiles_n * splits;
+  pdl_launch_dependents();      // after the TMEM allocation: a successor CTA sharing this SM can never starve this one
+  pdl_wait();                   // everything above ran under the previous kernel's tail; global memory from here on
 
   if (warp == EPI2_WARPS) {
     // =============================== TMA producer (both CTAs; whole warp, elected issue) ===============================
@@ -319,8 +321,8 @@ int launch2(const sc_gemm_desc* d, const CUtensorMap& ta, const CUtensorMap& tb,
   const int items = tiles_m * tiles_n * splits;
   const int max_pairs = sc_num_sms() / 2;
   const int pairs = items < max_pairs ? items : max_pairs;
-  kern<<<2 * pairs, THREADS2, SMEM2_BYTES, st>>>(ta, tb, tc_, tc2_, tx_, tiles_m, tiles_n, splits, kb_total, kb_per, ep);
-  SC_LAUNCH_CHECK();
+  SC_CUDA(sc_launch_pdl(kern, dim3(2 * pairs), dim3(THREADS2), SMEM2_BYTES, st, ta, tb, tc_, tc2_, tx_, tiles_m, tiles_n, splits,
+                        kb_total, kb_per, ep));
   return SC_OK;
 }
 

@@ -33,6 +33,8 @@ SC_DEVINL long remap_row(long r, int in_group, int out_group, int out_off) {
 
 template <typename TX, typename TY, int NV>
 __global__ void __launch_bounds__(256) ln_fwd_kernel(sc_ln_desc d) {
+  pdl_launch_dependents();      // programmatic dependent launch (common.cuh)
+  pdl_wait();
   const int lane = threadIdx.x & 31;
   const long row = (long)blockIdx.x * 8 + (threadIdx.x >> 5);
   if (row >= d.rows) return;
@@ -205,6 +207,8 @@ constexpr int LNB_WARPS = 4;
 template <typename TDY, typename TX, typename TDX, int NV8, bool CS>
 __global__ void __launch_bounds__(LNB_WARPS * 32, NV8 >= 4 ? 2 : 3) ln_bwd8_kernel(sc_ln_bwd_desc d) {
   __shared__ float red[LNB_WARPS][1024];
+  pdl_launch_dependents();      // programmatic dependent launch (common.cuh)
+  pdl_wait();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int D8 = d.D >> 3;
   const bool want_param = d.dgamma != nullptr;
@@ -304,8 +308,8 @@ int launch_bwd8(const sc_ln_bwd_desc& d, cudaStream_t st) {
   const long per_sm = nv >= 4 ? 2 : 3;                                         // resident CTAs per SM (register budget)
   const int grid = (int)(g < per_sm * sc_num_sms() ? g : per_sm * sc_num_sms());
 #define SC_LN8_CASE(NV_)                                                                     \
-  if (d.dx_colsum) ln_bwd8_kernel<TDY, TX, TDX, NV_, true><<<grid, LNB_WARPS * 32, 0, st>>>(d); \
-  else ln_bwd8_kernel<TDY, TX, TDX, NV_, false><<<grid, LNB_WARPS * 32, 0, st>>>(d);
+  if (d.dx_colsum) sc_launch_pdl(ln_bwd8_kernel<TDY, TX, TDX, NV_, true>, dim3(grid), dim3(LNB_WARPS * 32), 0, st, d); \
+  else sc_launch_pdl(ln_bwd8_kernel<TDY, TX, TDX, NV_, false>, dim3(grid), dim3(LNB_WARPS * 32), 0, st, d);
   switch (nv) {
     case 1: SC_LN8_CASE(1); break;
     case 2: SC_LN8_CASE(2); break;
@@ -373,12 +377,14 @@ __global__ void __launch_bounds__(LNT_WARPS * 32, 2) ln_bwd_tma_kernel(sc_ln_bwd
   float* gam = (float*)lsm;
   uint8_t* ring = lsm + D * 4 + (size_t)warp * LNT_STAGES * slot_bytes;
   uint64_t* bars = (uint64_t*)(lsm + D * 4 + (size_t)LNT_WARPS * LNT_STAGES * slot_bytes) + warp * LNT_STAGES;
-  for (int i = threadIdx.x; i < D; i += LNT_WARPS * 32) gam[i] = d.gamma[i];
+  pdl_launch_dependents();      // programmatic dependent launch (common.cuh): barrier init under the previous kernel's tail
   if (lane == 0) {
     for (int s = 0; s < LNT_STAGES; ++s)
       asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(lnt_smem(&bars[s])) : "memory");
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
+  pdl_wait();
+  for (int i = threadIdx.x; i < D; i += LNT_WARPS * 32) gam[i] = d.gamma[i];
   __syncthreads();
   const long stride = (long)gridDim.x * LNT_WARPS;
   const long row0 = (long)blockIdx.x * LNT_WARPS + warp;
@@ -504,7 +510,7 @@ int launch_bwd_tma(const sc_ln_bwd_desc& d, cudaStream_t st) {
   {                                                                                                                      \
     static sc_device_once once;                                                                                          \
     if (once.first()) { cudaFuncSetAttribute(ln_bwd_tma_kernel<TDY, TX, TDX, NV_, CS_>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); once.done(); } \
-    ln_bwd_tma_kernel<TDY, TX, TDX, NV_, CS_><<<grid, LNT_WARPS * 32, smem, st>>>(d);                                    \
+    sc_launch_pdl(ln_bwd_tma_kernel<TDY, TX, TDX, NV_, CS_>, dim3(grid), dim3(LNT_WARPS * 32), smem, st, d);              \
   }
 #define SC_LNT_NV(NV_) if (d.dx_colsum) SC_LNT_CASE(NV_, true) else SC_LNT_CASE(NV_, false)
   switch (nv) {
@@ -523,7 +529,7 @@ template <typename TX, typename TY>
 int launch_fwd(const sc_ln_desc& d, cudaStream_t st) {
   const int nv = ceil_div(d.D, 128);
   const int grid = ceil_div(d.rows, 8);
-#define SC_LN_CASE(NV_) ln_fwd_kernel<TX, TY, NV_><<<grid, 256, 0, st>>>(d)
+#define SC_LN_CASE(NV_) sc_launch_pdl(ln_fwd_kernel<TX, TY, NV_>, dim3(grid), dim3(256), 0, st, d)
   switch (nv) {
     case 1: SC_LN_CASE(1); break;
     case 2: SC_LN_CASE(2); break;
