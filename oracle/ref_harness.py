@@ -173,7 +173,7 @@ def build_reference_model(cfg, rank=0, world=1, kv_layout="torch18_flat"):
         first_stage_layer=cfg["first_stage_layer"],
         use_vision_mae_recon=cfg["use_mae"], use_text_mae_recon=False,
         use_seglabel=cfg["use_kl"], max_words=cfg["context"],
-        mae_vis_mask_ratio=0.75, mae_seq_mask_ratio=0.15)
+        mae_vis_mask_ratio=cfg.get("mae_vis_mask_ratio", 0.75), mae_seq_mask_ratio=0.15)
     model = SegCLIP(fake_clip_state_dict(cfg), args).float().train()
     return model
 

@@ -188,7 +188,7 @@ def make_batch(cfg, batch, seed=0, rank=0):
         ids[b, 0, 0] = V - 2                                   # SOT
         ids[b, 0, 1:1 + n] = torch.randint(1, V - 2, (n,), generator=g)
         ids[b, 0, 1 + n] = V - 1                               # EOT = unique arg-max
-    keep = int((L + 1) * 0.25) - 1
+    keep = int((L + 1) * (1 - cfg.get("mae_vis_mask_ratio", 0.75))) - 1      # module_clip_util.py:98, CLS dropped
     noise = dict(u1=torch.rand(batch, NUM_CENTERS, L, generator=g),
                  u2=torch.rand(batch, L + 1, generator=g),
                  u3=torch.rand(batch, NUM_CENTERS, keep, generator=g))
@@ -387,7 +387,7 @@ def encode_image_mae(image, p, cfg, u2, u3, kv_layout, forced_idx=None):
     t = "clip.visual.transformer."
     heads = cfg["vision_width"] // 64
     x = patch_embed(image, p, cfg)
-    x, mask, ids_restore, _ = random_masking_keep_cls(x, u2)
+    x, mask, ids_restore, _ = random_masking_keep_cls(x, u2, cfg.get("mae_vis_mask_ratio", 0.75))
     x = x[:, 1:]
     for i in range(cfg["first_stage_layer"]):
         x = self_attn_block(x, p, f"{t}layers0.{i}.", heads)

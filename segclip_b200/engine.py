@@ -94,7 +94,8 @@ class Engine:
         self.fsl = c["first_stage_layer"]
         self.n2 = 12 - self.fsl
         self.dd = self.vw // 2
-        self.keep = int((self.Lp + 1) * 0.25)
+        # kept tokens of the masked pass, CLS included: int(L * (1 - mask_ratio)) like module_clip_util.py:98
+        self.keep = int((self.Lp + 1) * (1 - c.get("mae_vis_mask_ratio", 0.75)))
         self.Lm = self.keep - 1
         self.use_mae, self.use_kl = bool(c["use_mae"]), bool(c["use_kl"])
         self.text_layers = c["text_layers"]

@@ -286,7 +286,10 @@ class SegCLIP(nn.Module):
         self.use_seglabel = self.cfg["use_kl"]
         self.use_text_mae_recon = False
         self.vis_mask_ratio = get_attr(task_config, "mae_vis_mask_ratio", 0.75)
-        assert abs(self.vis_mask_ratio - 0.75) < 1e-9, "only mae_vis_mask_ratio=0.75 (reference default) is built"
+        if not 0.0 < self.vis_mask_ratio < 1.0:
+            raise ValueError("mae_vis_mask_ratio must be in (0, 1), got %r" % (self.vis_mask_ratio,))
+        if self.vis_mask_ratio != 0.75:
+            self.cfg["mae_vis_mask_ratio"] = float(self.vis_mask_ratio)
         import weakref
         self.add_module("clip", _ClipFacade())
         self.clip.__dict__["_owner"] = weakref.ref(self)

@@ -50,6 +50,21 @@ def test_bf16_teacher_forced(case):
     assert rels[-1] <= 0.15, r["worst"][:5]
 
 
+@pytest.mark.parametrize("geometry,ratio,B", [("toy", 0.5, 3), ("toy", 0.3, 3), ("vitb16", 0.6, 2)])
+def test_other_mae_mask_ratios(geometry, ratio, B):
+    """`mae_vis_mask_ratio` != 0.75 (modules/modeling.py:142-145): the masked pass keeps int(L * (1 - ratio)) tokens
+    (module_clip_util.py:98); fp32 mode against the oracle, which is pinned to the reference at these ratios
+    (tests/test_oracle_vs_reference.py::test_other_mae_mask_ratios_match_reference)."""
+    from oracle import segclip_oracle as so
+    from tools.e2e_report import run_config
+    cfg = so.toy_config(use_mae=True, use_kl=True) if geometry == "toy" else so.vit_b16_config(use_mae=True, use_kl=True)
+    cfg["mae_vis_mask_ratio"] = ratio
+    r = run_config(cfg, B, 11, 12, "fp32", verbose=False, name="mask_ratio_%s" % ratio)
+    assert r["loss_rel"] <= 1e-3, r["loss_rel"]
+    assert r["assign_flip_rate"] == 0.0 and r["assign_flip_rate_mae"] == 0.0
+    assert r["max_grad_rel"] <= 1e-3, r["worst"][:5]
+
+
 PROD_CASES = {      # name: (batch, heads, kv_layout) -- ViT-B/16, M = B*196 >= 512: the benchmark's kernel dispatch
     "b8_contrastive_flat": (8, False, "torch18_flat"),
     "b16_heads_flat": (16, True, "torch18_flat"),

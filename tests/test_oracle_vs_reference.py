@@ -40,6 +40,23 @@ def test_toy_loss_and_grads_match_reference(kv_layout, heads_on):
             assert float(g.abs().max()) == 0.0, name
 
 
+@pytest.mark.parametrize("ratio", [0.5, 0.3])
+def test_other_mae_mask_ratios_match_reference(ratio):
+    """`mae_vis_mask_ratio` other than the recipe's 0.75 (modules/modeling.py:142-145, module_clip_util.py:98): the masked pass
+    keeps int(L * (1 - ratio)) tokens."""
+    cfg = so.toy_config(use_mae=True, use_kl=True)
+    cfg["mae_vis_mask_ratio"] = ratio
+    model = rh.build_reference_model(cfg)
+    params = so.init_params(cfg, seed=7)
+    model.load_state_dict(params, strict=False)
+    batch, noise = so.make_batch(cfg, 3, seed=8)
+    ref_loss, ref_grads = rh.run_reference(model, batch, noise, True)
+    loss, grads, _ = so.loss_and_grads(params, batch, noise, cfg, "torch18_flat", frozen=("vis_mae_decoder.decoder_pos_embed",))
+    assert abs(float(loss) - float(ref_loss)) <= 2e-5 * abs(float(ref_loss)), (float(loss), float(ref_loss))
+    for name, g in ref_grads.items():
+        assert _rel(grads[name], g) < 2e-4, (name, _rel(grads[name], g))
+
+
 def test_eval_mode_encoders_match_reference():
     """Inference path: eval-mode encode_image / encode_text of the reference (plain softmax assignment,
     modules/module_seg_vit.py:230-231) against the oracle's eval functions."""

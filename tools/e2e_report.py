@@ -23,7 +23,7 @@ from tests.golden_util import load_case       # noqa: E402
 def build_model(cfg, params, precision, kv_layout):
     args = argparse.Namespace(local_rank=0, rank=0, world_size=1, first_stage_layer=cfg["first_stage_layer"],
                               use_vision_mae_recon=cfg["use_mae"], use_seglabel=cfg["use_kl"], precision=precision,
-                              kv_layout=kv_layout)
+                              kv_layout=kv_layout, mae_vis_mask_ratio=cfg.get("mae_vis_mask_ratio", 0.75))
     model = SegCLIP(rh.fake_clip_state_dict(cfg), args)
     missing, unexpected = model.load_state_dict(params, strict=False)
     assert not missing and not unexpected, (missing, unexpected)
