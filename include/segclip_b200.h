@@ -51,6 +51,7 @@ long long sc_launch_count(void);
 #define SC_K_ATTN_BWD_TC 4  /* tcgen05 attention backward */
 #define SC_K_ATTN_MMA 5     /* mma.sync attention (legacy tensor path) */
 #define SC_K_ATTN_GENERIC 6 /* exact fp32 attention */
+#define SC_K_GEMM_TC2_TAIL 7 /* gemm_tc2_kernel launches whose incomplete last wave ran as column slices (counted in addition to kind 0) */
 #define SC_K_COUNT 8
 long long sc_kernel_launches(int kind);
 

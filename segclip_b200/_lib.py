@@ -141,7 +141,8 @@ def launch_count():
     return int(lib().sc_launch_count())
 
 
-KERNEL_KINDS = {"gemm_tc2": 0, "gemm_tc1": 1, "gemm_simt": 2, "attn_fwd_tc": 3, "attn_bwd_tc": 4, "attn_mma": 5, "attn_generic": 6}
+KERNEL_KINDS = {"gemm_tc2": 0, "gemm_tc1": 1, "gemm_simt": 2, "attn_fwd_tc": 3, "attn_bwd_tc": 4, "attn_mma": 5, "attn_generic": 6,
+                "gemm_tc2_tail": 7}
 
 
 def kernel_launches():

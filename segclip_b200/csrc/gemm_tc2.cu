@@ -11,6 +11,8 @@
 // Everything else (operand layouts, split-K, fused epilogues) is identical to gemm_tc.cu.
 #include "gemm_tc_common.cuh"
 
+extern void sc_count_kernel(int kind, int n);
+
 namespace {
 using namespace tc;
 
@@ -29,6 +31,9 @@ constexpr int A2_BYTES = 128 * BK * 2;
 constexpr int B2_BYTES = 128 * BK * 2;
 constexpr int STAGE2_BYTES = A2_BYTES + B2_BYTES;
 constexpr int SMEM2_BYTES = STAGES2 * STAGE2_BYTES + EPI2_WARPS * EPI2_STAGE_BYTES + 256 + EPI2_WARPS * 4 * 8;   // + input-tile mbarriers
+#ifndef SC_TC2_MAX_SHIFT_BMN
+#define SC_TC2_MAX_SHIFT_BMN 2      // column slices of an MN-major B operand: 2^shift per tile (64 columns = 32 per CTA at 2)
+#endif
 constexpr uint32_t PEER_MASK = 0xFEFFFFFFu;   // clears the CTA-rank bit of a shared::cluster address -> CTA 0 of the pair
 
 SC_DEVINL uint32_t cluster_ctarank() {
@@ -75,7 +80,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS2, 1)
 gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                 const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmC2,
                 const __grid_constant__ CUtensorMap tmX, int tiles_m, int tiles_n,
-                int splits, int kb_total, int kb_per_split, EpiParams ep) {
+                int splits, int kb_total, int kb_per_split, int full_items, int sub_shift, EpiParams ep) {
   extern __shared__ __align__(1024) uint8_t smem[];
   if ((smem_u32(smem) & 1023u) != 0u) __trap();
   uint8_t* smem_a = smem;
@@ -124,7 +129,27 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   cluster_sync_all();
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const int num_items = tiles_m * tiles_n * splits;
+  // Work items.  The first `full_items` are whole 256 x 256 tiles (x split-K slices); the tiles of an incomplete last wave
+  // (splits == 1 only) are cut into 2^sub_shift column slices so that the tail is spread over all CTA pairs instead of
+  // running on a few of them at full-tile cost (text tower: 154 tiles on 74 pairs = 3 waves for 2.08 of work -> 2.25).
+  const int num_items = full_items + ((tiles_m * tiles_n * splits - full_items) << sub_shift);
+  struct Item { int mt, nt, sp, ncol0, ncols; };
+  auto decode = [&](int item) {
+    Item t;
+    int tile = item, q = 0;
+    t.ncols = 256;
+    if (item >= full_items) {
+      const int j = item - full_items;
+      tile = full_items + (j >> sub_shift);
+      q = j & ((1 << sub_shift) - 1);
+      t.ncols = 256 >> sub_shift;
+    }
+    t.nt = tile % tiles_n;
+    t.mt = (tile / tiles_n) % tiles_m;
+    t.sp = tile / (tiles_n * tiles_m);
+    t.ncol0 = t.nt * 256 + q * t.ncols;
+    return t;
+  };
   pdl_launch_dependents();      // after the TMEM allocation: a successor CTA sharing this SM can never starve this one
   pdl_wait();                   // everything above ran under the previous kernel's tail; global memory from here on
 
@@ -139,11 +164,10 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       int stage = 0;
       uint32_t phase = 0;
       for (int item = pair; item < num_items; item += npairs) {
-        const int nt = item % tiles_n;
-        const int mt = (item / tiles_n) % tiles_m;
-        const int sp = item / (tiles_n * tiles_m);
-        const int m0 = mt * 256 + rank * 128, n0 = nt * 256 + rank * 128;
-        const int kb0 = sp * kb_per_split;
+        const Item t = decode(item);
+        // each CTA stages its half of the item's columns (a 128-row box whatever the slice width: a narrow slice reads ahead)
+        const int m0 = t.mt * 256 + rank * 128, n0 = t.ncol0 + rank * (t.ncols >> 1);
+        const int kb0 = t.sp * kb_per_split;
         const int kb1 = min(kb_total, kb0 + kb_per_split);
         // (prefetching the next tile's operands into L2 from here was measured on B200: -15 % on the K = 768 shapes)
         for (int kb = kb0; kb < kb1; ++kb) {
@@ -170,16 +194,17 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   } else if (warp == EPI2_WARPS + 1) {
     // =============================== MMA issuer (leader CTA only; whole warp, elected issue) ===============================
     if (rank == 0) {
-      constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((A_MN ? 1u : 0u) << 15) | ((B_MN ? 1u : 0u) << 16) |
-                                 ((uint32_t)(256 >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+      constexpr uint32_t idesc0 = (1u << 4) | (1u << 7) | (1u << 10) | ((A_MN ? 1u : 0u) << 15) | ((B_MN ? 1u : 0u) << 16) |
+                                  ((uint32_t)(256 >> 4) << 24);
       constexpr uint32_t a_kstep = A_MN ? (16 * 128) >> 4 : (16 * 2) >> 4;
       constexpr uint32_t b_kstep = B_MN ? (16 * 128) >> 4 : (16 * 2) >> 4;
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
       for (int item = pair; item < num_items; item += npairs, ++it) {
-        const int sp = item / (tiles_n * tiles_m);
-        const int kb0 = sp * kb_per_split;
+        const Item t = decode(item);
+        const uint32_t idesc = idesc0 | ((uint32_t)(t.ncols >> 3) << 17);      // N of the pair's MMA = slice width
+        const int kb0 = t.sp * kb_per_split;
         const int kb1 = min(kb_total, kb0 + kb_per_split);
         const int acc = it & 1;
         const uint32_t acc_phase = (it >> 1) & 1;
@@ -211,12 +236,12 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     float dotacc = 0.f;              // EF_ROWDOT: running per-head row dot of this lane's row
     int it = 0;
     for (int item = pair; item < num_items; item += npairs, ++it) {
-      const int nt = item % tiles_n;
-      const int mt = (item / tiles_n) % tiles_m;
-      const int nbase = nt * 256 + cgrp * EPI2_COLS;
+      const Item t = decode(item);
+      const int nbase = t.ncol0 + cgrp * EPI2_COLS;
+      const int nlim = min(ep.N, t.ncol0 + t.ncols);      // a column slice ends before the tile does (multiple of 64)
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
-      const int mrow0 = mt * 256 + rank * 128 + quarter * 32;
+      const int mrow0 = t.mt * 256 + rank * 128 + quarter * 32;
       float4 breg = make_float4(0.f, 0.f, 0.f, 0.f);
       if constexpr ((EpiTma<EF>::value || kIn) && (EF & EF_BIAS) != 0) {
         if (nbase + 4 * lane < ep.N) breg = __ldg((const float4*)(ep.bias + nbase + 4 * lane));
@@ -231,7 +256,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         __syncwarp();
 #pragma unroll
         for (int c = 0; c < NBOX; ++c)
-          if (nbase + c * 32 < ep.N && mrow0 < ep.M) issue_in(c);          // warp-uniform
+          if (nbase + c * 32 < nlim && mrow0 < ep.M) issue_in(c);          // warp-uniform
       }
       mbar_wait(&tmem_full[acc], acc_phase);
       tcgen05_fence_after();
@@ -240,15 +265,16 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       for (int c = 0; c < EPI2_COLS / 32; ++c) {
         float v[32];
         const int n0 = nbase + c * 32;
+        if (n0 >= nlim) break;                                    // past the item's column slice / the matrix (warp-uniform)
         if constexpr (kIn) {
           tmem_ld32(taddr + c * 32, v);
-          if (n0 < ep.N && mrow0 < ep.M) {                        // warp-uniform
+          if (n0 < nlim && mrow0 < ep.M) {                        // warp-uniform
             const int bx = c % NBOX;
             mbar_wait(&aux_bar[warp * 4 + bx], (aux_phase >> bx) & 1u);
             aux_phase ^= 1u << bx;
             if constexpr (kAux) epi_finish_aux_tma<EF>(ep, v, stage + bx * BOXB, lane, mrow0, n0, c, breg, &tmC, dotacc);
             else epi_finish_res_tma<EF>(ep, v, stage + bx * BOXB, lane, mrow0, n0, c, breg, &tmC);
-            if (NBOX < 4 && c + NBOX < 4 && n0 + NBOX * 32 < ep.N) {      // box reused within the tile (fp32 boxes)
+            if (NBOX < 4 && c + NBOX < 4 && n0 + NBOX * 32 < nlim) {      // box reused within the tile (fp32 boxes)
               bulk_wait_read<0>();
               __syncwarp();
               issue_in(c + NBOX);
@@ -321,8 +347,29 @@ int launch2(const sc_gemm_desc* d, const CUtensorMap& ta, const CUtensorMap& tb,
   const int items = tiles_m * tiles_n * splits;
   const int max_pairs = sc_num_sms() / 2;
   const int pairs = items < max_pairs ? items : max_pairs;
+  // Incomplete last wave (no split-K): cut its tiles into 2 or 4 column slices when that shortens the schedule.  An item
+  // costs its k-blocks x the slice's share of the MMA time + a fixed part (pipeline fill, epilogue tail) of ~3 k-blocks.
+  int full_items = items, sub_shift = 0;
+  const int rem = items % pairs;
+  static const int tail_split = getenv("SC_GEMM_TAIL_SPLIT") ? atoi(getenv("SC_GEMM_TAIL_SPLIT")) : 1;
+  if (tail_split && splits == 1 && rem != 0 && items > pairs && (EF & (EF_ROWDOT | EF_ATOMIC)) == 0 && EF != EF_GENERIC) {
+    double best = kb_total + 3.0;
+    for (int sh = 1; sh <= 2; ++sh) {
+      if (B_MN && sh > SC_TC2_MAX_SHIFT_BMN) break;
+      const int waves = ceil_div((long)rem << sh, pairs);
+      const double cost = waves * ((double)kb_total / (1 << sh) + 3.0);
+      if (cost < best * 0.9) {
+        best = cost;
+        sub_shift = sh;
+      }
+    }
+    if (sub_shift) {
+      full_items = items - rem;
+      sc_count_kernel(SC_K_GEMM_TC2_TAIL, 0);
+    }
+  }
   SC_CUDA(sc_launch_pdl(kern, dim3(2 * pairs), dim3(THREADS2), SMEM2_BYTES, st, ta, tb, tc_, tc2_, tx_, tiles_m, tiles_n, splits,
-                        kb_total, kb_per, ep));
+                        kb_total, kb_per, full_items, sub_shift, ep));
   return SC_OK;
 }
 

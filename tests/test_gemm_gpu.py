@@ -291,3 +291,47 @@ def test_forward_stores_activation_derivative_and_backward_multiplies(M, act):
     assert float((d_a.float() - want).abs().max() / want.abs().max()) < 1e-2
     ref = d_a.float().sum(0)
     assert float((cs - ref).abs().max()) < 2e-3 * (1 + float(ref.abs().max()))
+
+
+@pytest.mark.parametrize("M", [19712, 19712 + 13])
+def test_tc2_tail_column_slices(M):
+    """Incomplete last wave of the 2-CTA kernel run as 64-/128-column slices (text tower: 77 row tiles x N / 256 column tiles
+    on 74 CTA pairs): every hot epilogue kind, K-major and MN-major B, ragged last row tile."""
+    from segclip_b200 import _lib
+    if torch.cuda.get_device_properties(0).multi_processor_count != 148:
+        pytest.skip("shapes chosen for 74 CTA pairs")
+    k0 = _lib.kernel_launches()
+    bf = torch.bfloat16
+    _run(M, 512, 512, bf, bias=True, residual=True)                                        # out_proj: fp32 residual tile via TMA
+    _run(M, 512, 2048, bf, bias=True, residual=True, c_dtype=bf, res_dtype=bf)             # bf16 residual stream
+    _run(M, 512, 2048, bf, tb=True, c_dtype=bf)                                            # dgrad, MN-major B
+    _run(M, 512, 1536, bf, tb=True, c_dtype=bf, seed=3)
+    _run(M, 2048, 512, bf, bias=True, act=1, c_dtype=bf, c2=bf)                            # c_fc: two outputs, 24-tile tail
+    _run(M, 1536, 512, bf, bias=True, c_dtype=bf)                                          # qkv: 18-tile tail
+    _run(M, 512, 512, bf)                                                                  # plain fp32 output
+    _run(M, 512, 512, bf, tb=True, accumulate=True)                                        # fp32 C +=
+    k1 = _lib.kernel_launches()
+    assert k1["gemm_tc2_tail"] - k0["gemm_tc2_tail"] == 8, (k0, k1)
+
+
+def test_tc2_tail_slices_activation_gradient_with_colsum():
+    """Text c_proj dgrad: activation-derivative operand tile + fused bias-gradient column sums, with a sliced tail."""
+    from segclip_b200 import _lib, ops
+    if torch.cuda.get_device_properties(0).multi_processor_count != 148:
+        pytest.skip("shapes chosen for 74 CTA pairs")
+    torch.manual_seed(0)
+    M, N, K = 19712, 2048, 512
+    dy = torch.randn(M, K, device="cuda").bfloat16()
+    W = (torch.randn(K, N, device="cuda") * 0.05).bfloat16()
+    deriv = torch.rand(M, N, device="cuda").bfloat16()
+    out = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
+    cs = torch.zeros(N, device="cuda")
+    k0 = _lib.kernel_launches()
+    ops.gemm(dy, W, out, trans_b=True, mul_aux=deriv, mul_aux_act=ops.ACT_DERIV, colsum_out=cs)
+    torch.cuda.synchronize()
+    k1 = _lib.kernel_launches()
+    assert k1["gemm_tc2_tail"] - k0["gemm_tc2_tail"] == 1
+    want = (dy.float() @ W.float()) * deriv.float()
+    assert float((out.float() - want).abs().max() / want.abs().max()) < 1e-2
+    ref = out.float().sum(0)
+    assert float((cs - ref).abs().max()) < 2e-3 * (1 + float(ref.abs().max()))
