@@ -311,6 +311,11 @@ int sc_assign_fwd(const sc_assign_desc* a, void* stream);
 int sc_aggregate_fwd(const void* v, int v_dtype, const int32_t* idx, const float* count, const float* qf, float* agg,
                      float* sum_out, int B, int L, int D, void* stream);
 
+/* sc_assign_fwd + sc_aggregate_fwd as ONE kernel (one CTA per sample; the sample's key and value tiles are each read once,
+ * the patch's centre and the counts never leave shared memory).  `count` is written, not accumulated.  Same outputs as the
+ * two calls; shapes the fused kernel does not take fall back to them inside the call. */
+int sc_assign_aggregate_fwd(const sc_assign_desc* a, const void* v, int v_dtype, float* agg, float* sum_out, void* stream);
+
 /* Backward of the three steps above given d_agg = d(sum_out):
  *   d hard[g,l] = (<d_agg_g, v_l> - [count_g >= 1] <d_agg_g, agg_g>) / max(count_g,1) + d_hard_extra[g,l]
  *   d logits    = y_soft * (d hard - sum_c y_soft_c d hard_c) / tau           (straight-through, :237)

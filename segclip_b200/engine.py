@@ -494,12 +494,12 @@ class Engine:
             st_kln = ln_fwd(kfeat, s + "k_ln", k, tag + ".k_ln")
             y_soft, soft = buf(tag + ".y_soft", (Bn, G, Lx)), buf(tag + ".soft", (Bn, G, Lx))
             idx, count = buf(tag + ".idx", (Bn, Lx), i32), buf(tag + ".count", (Bn, G), zero=True)
-            fop = ops.assign_fwd_op(qf, k, u, y_soft, idx, count, Bn, Lx, D, TAU, None, soft)
-            fop_forced = ops.assign_fwd_op(qf, k, u, y_soft, idx, count, Bn, Lx, D, TAU, forced, soft)
-            fop_eval = ops.assign_fwd_op(qf, k, None, y_soft, idx, count, Bn, Lx, D, TAU, None, soft)
-            pl.f((fop, fop_forced, fop_eval))          # (training, teacher-forced, inference) variants
             agg, ssum = buf(tag + ".agg", (Mq, D)), buf(tag + ".sum", (Mq, D))
-            pl.f(ops.aggregate_fwd_op(vfeat, idx, count, qf, agg, ssum, Bn, Lx, D))
+            # assignment softmax + hard arg-max + per-centre weighted mean: ONE kernel, one CTA per sample (aggregate.cu)
+            fop = ops.assign_aggregate_fwd_op(qf, k, u, y_soft, idx, count, vfeat, agg, ssum, Bn, Lx, D, TAU, None, soft)
+            fop_forced = ops.assign_aggregate_fwd_op(qf, k, u, y_soft, idx, count, vfeat, agg, ssum, Bn, Lx, D, TAU, forced, soft)
+            fop_eval = ops.assign_aggregate_fwd_op(qf, k, None, y_soft, idx, count, vfeat, agg, ssum, Bn, Lx, D, TAU, None, soft)
+            pl.f((fop, fop_forced, fop_eval))          # (training, teacher-forced, inference) variants
             # proj_o = LN -> fc1 -> erf-GELU -> fc2 -> QuickGELU (module_seg_vit.py:271-275)
             hp = buf(tag + ".po_ln", (Mq, D), T)
             st_po = ln_fwd(ssum, s + "proj_o.ln", hp, tag + ".po_ln")

@@ -269,6 +269,18 @@ def assign_fwd_op(qf, k, u, y_soft, idx, count, B, Lp, D, tau=0.9, forced_idx=No
     return Op("sc_assign_fwd", (C.byref(a),), (a, qf, k, u, y_soft, idx, count, forced_idx, soft, logits))
 
 
+def assign_aggregate_fwd_op(qf, k, u, y_soft, idx, count, v, agg, sum_out, B, Lp, D, tau=0.9, forced_idx=None, soft=None,
+                            logits=None):
+    """assign_fwd_op + aggregate_fwd_op as one kernel (sc_assign_aggregate_fwd)."""
+    a = L.AssignDesc()
+    a.B, a.G, a.L, a.D = B, 8, Lp, D
+    a.qf, a.k, a.k_dtype, a.u, a.tau = qf.data_ptr(), k.data_ptr(), L.dt(k), _p(u), tau
+    a.forced_idx, a.logits, a.soft = _p(forced_idx), _p(logits), _p(soft)
+    a.y_soft, a.idx, a.count = y_soft.data_ptr(), idx.data_ptr(), count.data_ptr()
+    return Op("sc_assign_aggregate_fwd", (C.byref(a), v.data_ptr(), L.dt(v), agg.data_ptr(), sum_out.data_ptr()),
+              (a, qf, k, u, y_soft, idx, count, forced_idx, soft, logits, v, agg, sum_out))
+
+
 def aggregate_fwd_op(v, idx, count, qf, agg, sum_out, B, Lp, D):
     return Op("sc_aggregate_fwd", (v.data_ptr(), L.dt(v), idx.data_ptr(), count.data_ptr(), qf.data_ptr(), agg.data_ptr(),
                                    sum_out.data_ptr(), B, Lp, D), (v, idx, count, qf, agg, sum_out))

@@ -141,6 +141,63 @@ def test_assignment_aggregation_fwd_bwd(empty_center):
     assert _rel(d_v.view(B, Lx, D), vr.grad) < 1e-4
 
 
+@pytest.mark.parametrize("B,Lx,D,vdt", [(3, 196, 768, torch.bfloat16), (2, 48, 768, torch.float32), (5, 19, 128, torch.bfloat16),
+                                        (2, 256, 1024, torch.bfloat16), (1, 784, 768, torch.float32)])
+def test_fused_assign_aggregate_kernel(B, Lx, D, vdt):
+    """sc_assign_aggregate_fwd (assignment softmax + arg-max + weighted mean in ONE kernel, one CTA per sample) against the
+    two-kernel path, and the one-kernel backward behind sc_assign_bwd against autograd of the oracle's formulation."""
+    from segclip_b200 import ops
+    torch.manual_seed(B * Lx + D)
+    G = 8
+    qf, k = torch.randn(B, G, D) / D ** 0.25, torch.randn(B, Lx, D) / D ** 0.25
+    v = torch.randn(B, Lx, D).to(vdt).float()
+    u, extra, d_out = torch.rand(B, G, Lx), torch.randn(B, G, Lx) * 0.1, torch.randn(B, G, D)
+    qd, kd, vd, ud = qf.to(DEV).view(-1, D), k.to(DEV).view(-1, D), v.to(DEV).to(vdt).view(-1, D), u.to(DEV)
+
+    def outs():
+        return dict(y=torch.empty(B, G, Lx, device=DEV), soft=torch.empty(B, G, Lx, device=DEV),
+                    idx=torch.empty(B, Lx, device=DEV, dtype=torch.int32), count=torch.zeros(B, G, device=DEV),
+                    agg=torch.empty(B * G, D, device=DEV), ssum=torch.empty(B * G, D, device=DEV))
+    a, f = outs(), outs()
+    ops.assign_fwd_op(qd, kd, ud, a["y"], a["idx"], a["count"], B, Lx, D, 0.9, None, a["soft"])()
+    ops.aggregate_fwd_op(vd, a["idx"], a["count"], qd, a["agg"], a["ssum"], B, Lx, D)()
+    f["count"].fill_(7.0)                                    # written, not accumulated
+    ops.assign_aggregate_fwd_op(qd, kd, ud, f["y"], f["idx"], f["count"], vd, f["agg"], f["ssum"], B, Lx, D, 0.9, None, f["soft"])()
+    torch.cuda.synchronize()
+    flips = float((a["idx"] != f["idx"]).float().mean())
+    assert flips == 0.0, flips
+    assert torch.equal(a["count"], f["count"])
+    for key in ("y", "soft", "agg", "ssum"):
+        assert _rel(f[key], a[key]) < 1e-5, key
+    # inference variant (no Gumbel noise) and teacher forcing
+    forced = torch.randint(0, G, (B, Lx), device=DEV, dtype=torch.int32)
+    e = outs()
+    ops.assign_aggregate_fwd_op(qd, kd, None, e["y"], e["idx"], e["count"], vd, e["agg"], e["ssum"], B, Lx, D, 0.9, forced, e["soft"])()
+    torch.cuda.synchronize()
+    assert torch.equal(e["idx"], forced)
+    hard = torch.zeros(B, G, Lx, device=DEV).scatter_(1, forced.long().unsqueeze(1), 1.0)
+    want = torch.einsum("bgl,blc->bgc", hard, vd.float().view(B, Lx, D)) / hard.sum(-1, keepdim=True).clamp_min(1.0)
+    assert _rel(e["agg"].view(B, G, D), want) < 1e-5
+    # backward (fused kernel behind sc_assign_bwd) vs autograd
+    qr, kr, vr = (t.clone().requires_grad_(True) for t in (qf, k, v))
+    attn = torch.einsum("bgc,blc->bgl", qr, kr)
+    y = torch.softmax((attn + so.gumbel_from_uniform(u)) / 0.9, dim=1)
+    idx_ref = f["idx"].cpu().long()                          # the kernel's own arg-max (equal to the reference's up to exact ties)
+    hard = torch.zeros_like(y).scatter_(1, idx_ref.unsqueeze(1), 1.0) - y.detach() + y
+    out = torch.einsum("bgl,blc->bgc", hard, vr) / torch.clamp_min(hard.sum(-1, keepdim=True), 1.0)
+    ((qr + out) * d_out).sum().backward(retain_graph=True)
+    (hard * extra).sum().backward()
+    d_logits, d_v = torch.empty(B, G, Lx, device=DEV), torch.empty(B * Lx, D, device=DEV, dtype=vdt)
+    d_k, d_qf = torch.empty(B * Lx, D, device=DEV), torch.empty(B * G, D, device=DEV)
+    dsum = d_out.to(DEV).view(-1, D).contiguous()
+    ops.assign_bwd_op(dsum, f["agg"], vd, f["idx"], f["count"], f["y"], extra.to(DEV), qd, kd, d_logits, d_v, d_k, dsum, d_qf,
+                      B, Lx, D, 0.9)()
+    torch.cuda.synchronize()
+    assert _rel(d_qf.view(B, G, D), qr.grad) < 1e-4
+    assert _rel(d_k.view(B, Lx, D), kr.grad) < 1e-4
+    assert _rel(d_v.view(B, Lx, D), vr.grad) < (1e-2 if vdt == torch.bfloat16 else 1e-4)
+
+
 def test_reconstruct_layer_fwd_bwd():
     from segclip_b200 import ops
     torch.manual_seed(4)
