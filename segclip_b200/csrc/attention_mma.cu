@@ -405,7 +405,10 @@ bool sc_attn_mma_supported(const sc_attn_desc* a) {
 static int att_threads(int rows) {
   const int nblocks = (rows + 15) / 16;
   const int passes = (nblocks + AW - 1) / AW;
-  return ((nblocks + passes - 1) / passes) * 32;
+  const int t = ((nblocks + passes - 1) / passes) * 32;
+  // never fewer than four warps: with 8 centre queries a CTA had ONE warp to stage its 52 KB of K / V (cp.async), and an
+  // SM held four such warps -- the call was load-latency bound; the extra warps only stage, then leave the row loop
+  return t < 128 ? 128 : t;
 }
 
 int sc_attention_fwd_mma(const sc_attn_desc* a, cudaStream_t st) {

@@ -144,6 +144,41 @@ __global__ void im2col_kernel(const float* __restrict__ img, T* __restrict__ out
   }
 }
 
+// V consecutive pixels of a patch row per thread (V = 4 for patch 16: one 16-byte load, one 8- / 16-byte store; V = 2 for patch 14)
+template <typename T, int V>
+__global__ void __launch_bounds__(1024) im2col_vec_kernel(const float* __restrict__ img, T* __restrict__ out, long ld,
+                                                          const int* __restrict__ patch_idx, int rows_per_img, int grid_w, int p,
+                                                          int res_h, int res_w, long rows) {
+  const int KV = 3 * p * p / V;                      // vectors per row
+  const int per_cta = blockDim.x / KV;               // rows per CTA (host: blockDim.x = per_cta * KV)
+  const long row = (long)blockIdx.x * per_cta + threadIdx.x / KV;
+  if (row >= rows) return;
+  const int kv = threadIdx.x % KV;
+  const int b = row / rows_per_img;
+  const int pid = patch_idx ? patch_idx[row] : (int)(row % rows_per_img);
+  const int py0 = (pid / grid_w) * p, px0 = (pid % grid_w) * p;
+  const int k = kv * V;
+  const int c = k / (p * p), r = (k / p) % p, q = k % p;
+  const float* src = img + (((long)b * 3 + c) * res_h + py0 + r) * res_w + px0 + q;
+  T* dst = out + row * ld + k;
+  if constexpr (V == 4) {
+    const float4 x = *(const float4*)src;
+    if constexpr (sizeof(T) == 4) {
+      *(float4*)dst = x;
+    } else {
+      __nv_bfloat162 lo = __floats2bfloat162_rn(x.x, x.y), hi = __floats2bfloat162_rn(x.z, x.w);
+      uint2 u;
+      u.x = *(uint32_t*)&lo;
+      u.y = *(uint32_t*)&hi;
+      *(uint2*)dst = u;
+    }
+  } else {
+    const float2 x = *(const float2*)src;
+    if constexpr (sizeof(T) == 4) *(float2*)dst = x;
+    else *(__nv_bfloat162*)dst = __floats2bfloat162_rn(x.x, x.y);
+  }
+}
+
 // ---------------------------------------------------------------- bicubic resize of the positional table (inference)
 // VisualTransformer.get_pos_embed (modules/module_clip_vtransformer.py:35-53): F.interpolate(mode='bicubic',
 // align_corners=False) of the [g, g, D] patch table to [h, w, D].  Same arithmetic as ATen's upsample_bicubic2d: source
@@ -370,6 +405,21 @@ int sc_im2col(const float* image, void* out, int out_dtype, int64_t ld, const in
               int rows_per_img, int grid_h, int grid_w, int patch, void* stream) {
   SC_CHECK_ARG(image && out && rows > 0 && ld >= 3 * patch * patch && grid_h > 0 && grid_w > 0, "sc_im2col: bad args");
   sc_count_launch(1);
+  {
+    const int res_w = grid_w * patch, es = out_dtype == SC_F32 ? 4 : 2;
+    const int V = (patch % 4 == 0 && res_w % 4 == 0 && ld % 4 == 0) ? 4 : ((patch % 2 == 0 && res_w % 2 == 0 && ld % 2 == 0) ? 2 : 1);
+    const int KV = 3 * patch * patch / (V > 1 ? V : 1);
+    if (V > 1 && KV <= 1024 && ((uintptr_t)image & 15) == 0 && ((uintptr_t)out & 15) == 0 && (ld * es) % (V * es) == 0) {
+      const int per_cta = KV <= 256 ? 256 / KV : 1, threads = per_cta * KV;
+      const unsigned grid = (unsigned)((rows + per_cta - 1) / per_cta);
+#define SC_I2C(T_, V_) im2col_vec_kernel<T_, V_><<<grid, threads, 0, (cudaStream_t)stream>>>(image, (T_*)out, ld, patch_idx, rows_per_img, grid_w, patch, grid_h * patch, res_w, rows)
+      if (out_dtype == SC_F32) { if (V == 4) SC_I2C(float, 4); else SC_I2C(float, 2); }
+      else { if (V == 4) SC_I2C(bf16, 4); else SC_I2C(bf16, 2); }
+#undef SC_I2C
+      SC_LAUNCH_CHECK();
+      return SC_OK;
+    }
+  }
   if (out_dtype == SC_F32)
     im2col_kernel<float><<<(unsigned)rows, 256, 0, (cudaStream_t)stream>>>(image, (float*)out, ld, patch_idx, rows_per_img, grid_w, patch,
                                                                           grid_h * patch, grid_w * patch);
