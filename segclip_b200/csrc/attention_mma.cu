@@ -309,7 +309,7 @@ __global__ void __launch_bounds__(AT, 2) attn_bwd_dq_mma_kernel(sc_attn_bwd_desc
 
 // =================================================================================== backward: dK, dV
 template <int HD, bool CAUSAL>
-__global__ void __launch_bounds__(AT, 1) attn_bwd_dkv_mma_kernel(sc_attn_bwd_desc gd, const float* __restrict__ delta,
+__global__ void __launch_bounds__(AT, 2) attn_bwd_dkv_mma_kernel(sc_attn_bwd_desc gd, const float* __restrict__ delta,
                                                                  int lq_pad) {
   const sc_attn_desc& a = gd.fwd;
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -392,7 +392,7 @@ extern void sc_count_kernel(int kind, int n);
 
 // Whether the tensor-core kernels cover this problem (otherwise the generic fp32 kernels run).
 bool sc_attn_mma_supported(const sc_attn_desc* a) {
-  return a->dtype == SC_BF16 && (a->hd == 64 || a->hd == 48 || a->hd == 32) && a->Lq >= 1 && a->Lk >= 16 &&
+  return a->dtype == SC_BF16 && (a->hd == 64 || a->hd == 48 || a->hd == 32) && a->Lq >= 1 && a->Lk >= 1 &&
          a->Lq <= 1024 && a->Lk <= 1024 && a->B <= 65535 && a->H <= 65535 && aligned_for_mma(a);
 }
 
