@@ -269,6 +269,11 @@ int sc_text_embed(const int64_t* ids, const float* tok, const float* pos, float*
 /* out[r,:] = src[idx[r],:]; src in src_dtype (fp32, or the bf16 residual stream), out fp32 */
 int sc_gather_rows(const void* src, int src_dtype, const int32_t* idx, float* out, int64_t rows, int D, void* stream);
 int sc_scatter_rows(const float* src, const int32_t* idx, float* out, int64_t rows, int D, void* stream);
+/* out[idx[r] + idx_offset, :] += src[r, :] (fp32 atomics).  Backward of an embedding lookup: nn.Embedding of the token ids
+ * (modules/module_clip.py:107, idx int64) and the positional rows of the masked visual pass (module_clip_vtransformer.py:66-71,
+ * idx int32 patch index, idx_offset 1 for the CLS row) when the reference's frozen stem is trained. */
+int sc_scatter_add_rows(const void* src, int src_dtype, const void* idx, int idx_is_int64, int64_t idx_offset, float* out,
+                        int64_t rows, int D, void* stream);
 
 /* random_masking(keep_cls=True) (modules/module_clip_util.py:91-124) from an explicit uniform draw u
  * [B, L1]: ids_restore = argsort(argsort(noise)), ids_keep [B, keep], mask (1 = removed) and

@@ -262,6 +262,16 @@ __global__ void scatter_rows_kernel(const float* __restrict__ src, const int* __
   for (int d = threadIdx.x; d < D; d += blockDim.x) out[s * D + d] = src[r * D + d];
 }
 
+// out[idx[r] + idx_offset, :] += src[r, :] (fp32 atomics): gradient of an embedding lookup -- token embedding rows by token id
+// (int64), positional rows of the masked visual pass by patch index (int32)
+template <typename TI>
+__global__ void scatter_add_rows_kernel(const void* __restrict__ src, int sdt, const TI* __restrict__ idx, long idx_offset,
+                                        float* __restrict__ out, int D) {
+  const long r = blockIdx.x;
+  const long s = (long)idx[r] + idx_offset;
+  for (int d = threadIdx.x; d < D; d += blockDim.x) atomicAdd(out + s * D + d, ld_any(src, r * D + d, sdt));
+}
+
 // ---------------------------------------------------------------- MAE random masking by rank
 // ids_restore[b,i] = rank of noise[b,i] (noise[b,0] forced to -1); kept tokens have rank < keep.
 __global__ void mae_mask_kernel(const float* __restrict__ u, int L1, int keep, int* __restrict__ ids_restore,
@@ -469,6 +479,18 @@ int sc_scatter_rows(const float* src, const int32_t* idx, float* out, int64_t ro
   SC_CHECK_ARG(src && idx && out && rows > 0, "sc_scatter_rows: bad args");
   sc_count_launch(1);
   scatter_rows_kernel<<<(unsigned)rows, 128, 0, (cudaStream_t)stream>>>(src, idx, out, D);
+  SC_LAUNCH_CHECK();
+  return SC_OK;
+}
+
+int sc_scatter_add_rows(const void* src, int src_dtype, const void* idx, int idx_is_int64, int64_t idx_offset, float* out,
+                        int64_t rows, int D, void* stream) {
+  SC_CHECK_ARG(src && idx && out && rows > 0 && D > 0, "sc_scatter_add_rows: bad args");
+  sc_count_launch(1);
+  if (idx_is_int64)
+    scatter_add_rows_kernel<long long><<<(unsigned)rows, 128, 0, (cudaStream_t)stream>>>(src, src_dtype, (const long long*)idx, idx_offset, out, D);
+  else
+    scatter_add_rows_kernel<int><<<(unsigned)rows, 128, 0, (cudaStream_t)stream>>>(src, src_dtype, (const int*)idx, idx_offset, out, D);
   SC_LAUNCH_CHECK();
   return SC_OK;
 }

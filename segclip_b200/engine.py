@@ -40,6 +40,10 @@ MAE_BLOCK = dict(ln1="norm1", wqkv="attn.qkv.weight", bqkv="attn.qkv.bias", wo="
 FROZEN_STEM = ("clip.visual.class_embedding", "clip.visual.positional_embedding", "clip.visual.conv1.weight",
                "clip.visual.ln_pre.weight", "clip.visual.ln_pre.bias", "clip.positional_embedding",
                "clip.token_embedding.weight", "vis_mae_decoder.decoder_pos_embed")
+# ... of which the reference can train everything but the fixed sin-cos decoder table (requires_grad=False in the reference
+# itself, module_mae.py): an engine built with train_stem=True also produces the gradients of these (the reference computes
+# them whenever the recipe does not freeze the parameters)
+TRAINABLE_STEM = FROZEN_STEM[:-1]
 
 
 def _is_gemm_weight(name, t):
@@ -73,8 +77,9 @@ class Plan:
 
 
 class Engine:
-    def __init__(self, cfg, named_params, precision="bf16", kv_layout="torch18_flat", rank=0, world=1):
+    def __init__(self, cfg, named_params, precision="bf16", kv_layout="torch18_flat", rank=0, world=1, train_stem=False):
         assert precision in ("fp32", "bf16")
+        self.train_stem = bool(train_stem)
         assert kv_layout in ("torch18_flat", "per_sample")
         self.cfg = dict(cfg)
         self.precision = precision
@@ -111,7 +116,7 @@ class Engine:
     # ------------------------------------------------------------------ parameters
     def _setup_params(self):
         dev = self.dev
-        self._layout_grads([n for n in self.params if n not in FROZEN_STEM])
+        self._layout_grads([n for n in self.params if n not in FROZEN_STEM or (self.train_stem and n in TRAINABLE_STEM)])
         self._sig()
         # compute-dtype shadows of the GEMM weights (bf16 mode); fp32 mode reads the masters directly
         self.shadow = {}
@@ -533,9 +538,11 @@ class Engine:
             pl.b(grp)
             return sx, d_sx, idx
 
-        def vision_stem(tag, rows_per_img, patch_idx):
+        def vision_stem(tag, rows_per_img, patch_idx, d_x0=None):
             """conv1 (as GEMM) + positional embedding + ln_pre on patch tokens only: the CLS token is
-            discarded by SegViT (module_seg_vit.py:419) and all of this is frozen (F10)."""
+            discarded by SegViT (module_seg_vit.py:419), so class_embedding and positional row 0 receive a zero gradient.
+            The reference recipe freezes all of this (F10); with train_stem the backward of the stem is appended:
+            d_x0 = gradient of the stem output (the stream gradient after block 0's backward)."""
             v = "clip.visual."
             M = B * rows_per_img
             K = 3 * self.patch * self.patch
@@ -548,7 +555,24 @@ class Engine:
             pos = self.P(v + "positional_embedding")[1:] if self.pos_table is None else self.pos_table
             pl.f(ops.gemm_op(cols, self.conv_weight(), pre, rowbias=pos, rowbias_idx=patch_idx, rowbias_mod=self.Lp))
             x0 = buf(tag + ".x0", (M, self.vw))
-            pl.f(ops.layernorm_op(pre, self.P(v + "ln_pre.weight"), self.P(v + "ln_pre.bias"), x0))
+            if not (self.train_stem and d_x0 is not None):
+                pl.f(ops.layernorm_op(pre, self.P(v + "ln_pre.weight"), self.P(v + "ln_pre.bias"), x0))
+                return x0
+            st_pre = ln_fwd(pre, v + "ln_pre", x0, tag + ".ln_pre")
+            d_pre = sbuf("stem.d_pre", (M, self.vw), T)
+            grp = [ln_bwd(d_x0, pre, st_pre, v + "ln_pre", d_pre)]
+            # conv1.weight [width, 3, p, p] as [width, K]: dW += d_pre^T cols (K = 588 for patch 14: the padded im2col columns
+            # 588..591 are dropped by the GEMM's N)
+            gw = self.grads[v + "conv1.weight"].view(self.vw, K)
+            grp.append(ops.gemm_op(d_pre, cols[:, :K] if Kp != K else cols, gw, trans_a=True, trans_b=True, accumulate=True,
+                                   split_k=-1))
+            # positional rows 1..: sum over the batch (all patches present) / scatter by patch index (masked pass)
+            gpos = self.grads[v + "positional_embedding"]
+            if patch_idx is None:
+                grp.append(ops.colsum_op(d_pre, gpos[1:].reshape(-1), rows=B, cols=rows_per_img * self.vw, ld=rows_per_img * self.vw))
+            else:
+                grp.append(ops.scatter_add_rows_op(d_pre, patch_idx, gpos, idx_offset=1))
+            pl.b(grp)
             return x0
 
         t_ = "clip.visual.transformer."
@@ -562,6 +586,10 @@ class Engine:
                                self.Tctx, W_))
         dxt = buf("t.dx", (Mt, W_), zero=True)          # fp32 landing buffer of the EOT-row scatter; the blocks use dxtT only
         dxtT = tcopy("t.dxT", dxt)
+        if self.train_stem:
+            # x0 = token_embedding[ids] + positional_embedding (module_clip.py:107-109): after block 0's backward dxtT is d x0
+            pl.b([ops.colsum_op(dxtT, self.grads["clip.positional_embedding"].view(-1), rows=B, cols=self.Tctx * W_, ld=self.Tctx * W_),
+                  ops.scatter_add_rows_op(dxtT, ids.view(-1), self.grads["clip.token_embedding.weight"])])
         hd_ = None
         for i in range(self.text_layers):
             xt, hd_ = block(xt, dxtT, dxtT, f"clip.transformer.resblocks.{i}.", CLIP_BLOCK, f"t{i}", B, self.Tctx, self.Ht, True,
@@ -587,9 +615,9 @@ class Engine:
 
         # =============================================================== vision tower, main pass
         pl.f("wait_image")        # the image H2D copy runs on a side stream underneath the text tower
-        xv = vision_stem("v.stem", self.Lp, None)
         Mv = B * self.Lp
         dxv = buf("v.dx", (Mv, D), T)          # gradient of the layers0 stream; first written (not accumulated) by semantic()
+        xv = vision_stem("v.stem", self.Lp, None, dxv)
         hd_ = None
         for i in range(self.fsl):
             xv, hd_ = block(xv, dxv, dxv, f"{t_}layers0.{i}.", CLIP_BLOCK, f"v{i}", B, self.Lp, self.Hv, prev=hd_)
@@ -673,9 +701,9 @@ class Engine:
             ids_restore, ids_keep = buf("m.ids_restore", (B, L1), i32), buf("m.ids_keep", (B, keep), i32)
             mask, pidx = buf("m.mask", (B, L1)), buf("m.pidx", (B * Lm,), i32)
             pl.f(ops.mae_mask_op(u2, ids_restore, ids_keep, mask, pidx, B, L1, keep))
-            xm = vision_stem("m.stem", Lm, pidx)
             Mm = B * Lm
             dxm = buf("m.dx", (Mm, D), T)
+            xm = vision_stem("m.stem", Lm, pidx, dxm)
             hd_ = None
             for i in range(self.fsl):
                 xm, hd_ = block(xm, dxm, dxm, f"{t_}layers0.{i}.", CLIP_BLOCK, f"m{i}", B, Lm, self.Hv, prev=hd_)

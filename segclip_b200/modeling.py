@@ -17,7 +17,7 @@ from torch import nn
 
 from . import _lib as L
 from . import ops
-from .engine import DEC_DEPTH, FROZEN_STEM, Engine, G
+from .engine import DEC_DEPTH, FROZEN_STEM, TRAINABLE_STEM, Engine, G
 
 
 def get_attr(cfg, name, default):
@@ -346,14 +346,23 @@ class SegCLIP(nn.Module):
 
     # ---- engine plumbing -------------------------------------------------------------------------
     def _get_engine(self):
-        if self._engine is None or self._engine.params_moved():
+        named = None
+        if self._engine is not None:
+            # the stem the reference recipe freezes (main_task_align.py:389-441) was (un)frozen since the engine was built:
+            # rebuild it with / without the stem's backward
             named = dict(self.named_parameters())
+            if self._engine.train_stem != any(named[n].requires_grad for n in TRAINABLE_STEM):
+                assert self._sync_group is None or not self._engine.plans, "(un)freeze the stem before the first step when the native gradient sync is on"
+                self._engine = None
+        if self._engine is None or self._engine.params_moved():
+            named = named or dict(self.named_parameters())
             dev = next(iter(named.values())).device
             if dev.type != "cuda":
                 raise L.SegclipB200Error("segclip_b200 has no CPU path: move the module to a CUDA device first")
             tc = self.task_config
             self._engine = Engine(self.cfg, named, self.precision, self.kv_layout, int(get_attr(tc, "rank", 0)),
-                                  int(get_attr(tc, "world_size", 1)))
+                                  int(get_attr(tc, "world_size", 1)),
+                                  train_stem=any(named[n].requires_grad for n in TRAINABLE_STEM))
             self._param_items = list(named.items())
             self._untouched = set()
             if not self.cfg["use_mae"]:
@@ -398,11 +407,6 @@ class SegCLIP(nn.Module):
         if not self.training:
             return None
         eng = self._get_engine()
-        for name, p in self._param_items:
-            if name in FROZEN_STEM and p.requires_grad:
-                raise NotImplementedError(
-                    "%s requires grad, but the B200 hot path keeps the stem frozen like the reference recipe "
-                    "(main_task_align.py:389-441)" % name)
         dev = eng.dev
         ids = torch.as_tensor(input_ids)
         ids = ids.view(-1, ids.shape[-1]).to(dev, non_blocking=True)

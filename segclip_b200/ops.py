@@ -239,6 +239,14 @@ def scatter_rows_op(src, idx, out):
     return Op("sc_scatter_rows", (src.data_ptr(), idx.data_ptr(), out.data_ptr(), src.shape[0], src.shape[1]), (src, idx, out))
 
 
+def scatter_add_rows_op(src, idx, out, idx_offset=0):
+    """out[idx[r] + idx_offset] += src[r] (embedding-lookup backward)."""
+    assert idx.dtype in (torch.int32, torch.int64) and idx.numel() == src.shape[0] and out.dtype == torch.float32
+    assert src.is_contiguous() and out.is_contiguous() and out.shape[-1] == src.shape[1]
+    return Op("sc_scatter_add_rows", (src.data_ptr(), L.dt(src), idx.data_ptr(), int(idx.dtype == torch.int64), idx_offset,
+                                      out.data_ptr(), src.shape[0], src.shape[1]), (src, idx, out))
+
+
 def mae_mask_op(u, ids_restore, ids_keep, mask, patch_idx, B, L1, keep):
     return Op("sc_mae_mask", (u.data_ptr(), B, L1, keep, ids_restore.data_ptr(), ids_keep.data_ptr(), mask.data_ptr(),
                               patch_idx.data_ptr()), (u, ids_restore, ids_keep, mask, patch_idx))

@@ -65,6 +65,41 @@ def test_other_mae_mask_ratios(geometry, ratio, B):
     assert r["max_grad_rel"] <= 1e-3, r["worst"][:5]
 
 
+@pytest.mark.parametrize("geometry,B,precision", [("toy", 3, "fp32"), ("vitb16", 2, "fp32"), ("vitl14ish", 2, "fp32"), ("vitb16", 8, "bf16")])
+def test_trained_stem_gradients(geometry, B, precision):
+    """The stem the reference RECIPE freezes (conv1, class / positional embeddings, ln_pre, token / positional text embedding;
+    main_task_align.py:389-441) trained after all: `requires_grad_(True)` on those parameters makes the engine append the
+    stem's backward (ln_pre backward, conv1 weight gradient, positional sums / scatters of both visual passes, token-embedding
+    scatter-add).  Against the oracle, which is pinned to the reference with these parameters trainable
+    (tests/test_oracle_vs_reference.py compares every gradient the unmodified reference produces)."""
+    from oracle import segclip_oracle as so
+    from tools.e2e_report import run_config
+    if geometry == "toy":
+        cfg = so.toy_config(use_mae=True, use_kl=True)
+    elif geometry == "vitb16":
+        cfg = so.vit_b16_config(use_mae=True, use_kl=True)
+    else:       # patch 14: 3 * 14 * 14 = 588 columns, im2col operand padded to 592
+        cfg = so.vit_b16_config(use_mae=True, use_kl=True)
+        cfg.update(patch=14, grid=8, vision_width=256, text_width=128, embed_dim=128, text_layers=2)
+    r = run_config(cfg, B, 5, 6, precision, forced=(precision == "bf16"), verbose=False, name="train_stem", train_stem=True,
+                   ideal=(precision == "bf16"))
+    stem = ("clip.visual.conv1.weight", "clip.visual.positional_embedding", "clip.visual.ln_pre.weight", "clip.visual.ln_pre.bias",
+            "clip.positional_embedding", "clip.token_embedding.weight", "clip.visual.class_embedding")
+    assert all(k in r["errs"] for k in stem), sorted(r["errs"])[:5]
+    if precision == "fp32":
+        assert r["loss_rel"] <= 1e-3
+        assert r["assign_flip_rate"] == 0.0
+        assert r["max_grad_rel"] <= 1e-3, r["worst"][:5]
+    else:
+        # bf16 production dispatch: the stem gradients against the irreducible operand-rounding error of the same oracle
+        # (oracle/bf16_emulation.py), like test_bf16_production_dispatch_matches_oracle does for the rest
+        assert r["loss_rel"] <= 1e-2
+        assert r["median_grad_rel"] <= 1.5 * r["ideal_median_grad_rel"] + 5e-3
+        for k in stem[:-1]:
+            assert r["errs"][k][1] >= 0.98, (k, r["errs"][k])
+            assert r["errs"][k][0] <= 2.0 * r["ideal_errs"][k] + 2e-2, (k, r["errs"][k], r["ideal_errs"][k])
+
+
 PROD_CASES = {      # name: (batch, heads, kv_layout) -- ViT-B/16, M = B*196 >= 512: the benchmark's kernel dispatch
     "b8_contrastive_flat": (8, False, "torch18_flat"),
     "b16_heads_flat": (16, True, "torch18_flat"),

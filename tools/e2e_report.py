@@ -38,14 +38,21 @@ def run_case(case, precision, forced=False, verbose=True):
     return out
 
 
-def run_config(cfg, B, param_seed, batch_seed, precision, forced=False, kv="torch18_flat", verbose=True, name="", ideal=False):
+def run_config(cfg, B, param_seed, batch_seed, precision, forced=False, kv="torch18_flat", verbose=True, name="", ideal=False,
+               train_stem=False):
     """CUDA path vs the CPU oracle on seeded inputs.  ``ideal=True`` additionally runs the oracle with every matrix-product
     operand rounded to bf16 (oracle/bf16_emulation.py) and reports its gradient error next to the CUDA path's."""
     from segclip_b200 import _lib
     params = so.init_params(cfg, seed=param_seed)
     batch, noise = so.make_batch(cfg, B, seed=batch_seed)
-    ref_loss, ref_grads, info = so.loss_and_grads(params, batch, noise, cfg, kv, frozen=FROZEN_STEM)
+    # train_stem: the parameters the reference recipe freezes are trained too (all but the fixed sin-cos decoder table)
+    frozen = FROZEN_STEM[-1:] if train_stem else FROZEN_STEM
+    ref_loss, ref_grads, info = so.loss_and_grads(params, batch, noise, cfg, kv, frozen=frozen)
     model = build_model(cfg, params, precision, kv)
+    if train_stem:
+        for n_, p_ in model.named_parameters():
+            if n_ in FROZEN_STEM[:-1]:
+                p_.requires_grad_(True)
     model.inject_noise({k: v.cuda() for k, v in noise.items()})
     if forced:
         f = {"main": info["assign_main"].cuda(), "pool": info["pool_arg"].cuda()}
@@ -70,7 +77,7 @@ def run_config(cfg, B, param_seed, batch_seed, precision, forced=False, kv="torc
     errs = {}
     grads = {}
     for name_, p in model.named_parameters():
-        if name_ in FROZEN_STEM:
+        if name_ in frozen:
             continue
         rg = ref_grads.get(name_)
         if p.grad is None:
@@ -95,7 +102,7 @@ def run_config(cfg, B, param_seed, batch_seed, precision, forced=False, kv="torc
         if cfg["use_mae"]:
             f["mae"] = info["assign_mae"]
         with BF16Operands():
-            il, ig, _ = so.loss_and_grads(params, batch, noise, cfg, kv, forced=f, frozen=FROZEN_STEM)
+            il, ig, _ = so.loss_and_grads(params, batch, noise, cfg, kv, forced=f, frozen=frozen)
         ideal_errs = {k: float((ig[k] - ref_grads[k]).norm()) / (float(ref_grads[k].norm()) + 1e-12) for k in ref_grads if k in ig}
         ir = sorted(ideal_errs.values())
         out["ideal_errs"] = ideal_errs
