@@ -27,6 +27,7 @@ class NvlsGradSync:
         self.timeout_ms = int(float(os.environ.get("SEGCLIP_P2P_TIMEOUT_S", "600")) * 1000)
         self.stream = torch.cuda.Stream(device=device)
         self.err = torch.zeros(1, device=device, dtype=torch.int32)
+        self.profile = None         # a list: all_reduce() appends (ready, start, end) CUDA events per bucket (tools/sync_timeline.py)
 
     @classmethod
     def create(cls, group, device):
@@ -72,11 +73,20 @@ class NvlsGradSync:
     def all_reduce(self, start, end, after_stream):
         """Mean over ranks of gflat[start:end] (element offsets, multiples of 4), in place on every rank.  Runs on the sync
         stream after everything already queued on `after_stream`; join() makes a stream wait for all issued reductions."""
+        prof = self.profile
+        if prof is not None:
+            ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+            ev[0].record(after_stream)               # the bucket's last writer has been issued before this point
         self.stream.wait_stream(after_stream)
+        if prof is not None:
+            ev[1].record(self.stream)
         rc = L.lib().sc_nvls_allreduce(self.mc + 4 * start, end - start, 1.0 / self.world, self.rank, self.world,
                                        self.peer_flags.data_ptr(), self.epoch, self.BLOCKS, self.timeout_ms,
                                        self.err.data_ptr(), self.stream.cuda_stream)
         L.check(rc, "sc_nvls_allreduce")
+        if prof is not None:
+            ev[2].record(self.stream)
+            prof.append(("bucket", 4 * (end - start), ev))
         self.epoch = (self.epoch + 2) & 0xFFFFFFFF
 
     def join(self, stream):

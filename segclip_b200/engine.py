@@ -952,7 +952,14 @@ class Engine:
         for w in works:
             w.wait()               # stream-level wait, the host does not block
         if nv is not None and pl.bucket_after:
-            nv.join(cur)
+            if nv.profile is not None:                 # tools/sync_timeline.py: how long the step waits for the reductions
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(cur)
+                nv.join(cur)
+                e1.record(cur)
+                nv.profile.append(("join", 0, (e0, e1)))
+            else:
+                nv.join(cur)
         return self.gflat
 
     def profile_gemm(self, B):
