@@ -13,6 +13,17 @@
 
 extern void sc_count_kernel(int kind, int n);
 
+#ifdef SC_GEMM_TRACE
+// debug build (-DSC_GEMM_TRACE, tools/trace_gemm.py): globaltimer at the start and the end of every CTA of the last launch --
+// how far apart the statically scheduled CTA pairs finish
+__device__ unsigned long long g_gemm_trace[2][256];
+SC_DEVINL unsigned long long gtimer() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+#endif
+
 namespace {
 using namespace tc;
 
@@ -152,6 +163,9 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   };
   pdl_launch_dependents();      // after the TMEM allocation: a successor CTA sharing this SM can never starve this one
   pdl_wait();                   // everything above ran under the previous kernel's tail; global memory from here on
+#ifdef SC_GEMM_TRACE
+  if (threadIdx.x == 0 && blockIdx.x < 256) g_gemm_trace[0][blockIdx.x] = gtimer();
+#endif
 
   if (warp == EPI2_WARPS) {
     // =============================== TMA producer (both CTAs; whole warp, elected issue) ===============================
@@ -299,6 +313,10 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   if constexpr (EpiTma<EF>::value || kIn) {
     if (warp < EPI2_WARPS) bulk_wait_all();                  // staging smem must outlive the last TMA stores
   }
+#ifdef SC_GEMM_TRACE
+  __syncthreads();
+  if (threadIdx.x == 0 && blockIdx.x < 256) g_gemm_trace[1][blockIdx.x] = gtimer();
+#endif
   tcgen05_fence_before();
   cluster_sync_all();
   if (warp == EPI2_WARPS + 1) {
@@ -439,3 +457,10 @@ int sc_gemm_tc2(const sc_gemm_desc* d, cudaStream_t st) {
   SC_L2(true, true, EF_GENERIC)
 #undef SC_L2
 }
+
+#ifdef SC_GEMM_TRACE
+extern "C" int sc_debug_gemm_trace(unsigned long long* out) {
+  cudaDeviceSynchronize();
+  return (int)cudaMemcpyFromSymbol(out, g_gemm_trace, sizeof(unsigned long long) * 2 * 256);
+}
+#endif
