@@ -66,16 +66,17 @@ SC_DEVINL void sts128u(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32
 
 // delta[b,h,i] = sum_d dO[b,i,h,d] * O[b,i,h,d]
 __global__ void attn_delta_kernel(const bf16* __restrict__ o, const bf16* __restrict__ d_o, long bs, long rs, int B, int H, int L,
-                                  float* __restrict__ delta) {
+                                  float* __restrict__ delta, int hd = HD) {
   const long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= (long)B * L * H) return;
   const int h = t % H;
   const long row = t / H;
   const int b = row / L, i = row % L;
-  const long off = (long)b * bs + (long)i * rs + h * HD;
+  const long off = (long)b * bs + (long)i * rs + h * hd;
   float s = 0.f;
 #pragma unroll
   for (int c = 0; c < HD / 8; ++c) {
+    if (c * 8 >= hd) break;
     const uint4 a = *(const uint4*)(o + off + c * 8), g = *(const uint4*)(d_o + off + c * 8);
     const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, gw[4] = {g.x, g.y, g.z, g.w};
 #pragma unroll
@@ -163,6 +164,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   const int L = a.Lq;
   const int ntile = (L + TILE - 1) / TILE;
   const int total = a.H * a.B;                       // work items: (sample, head), persistent CTAs stride over them
+  const bool pad = a.hd != HD;                       // head dim 32 / 48 in zero-padded 64-wide tiles (MAE decoder: 48)
 
   // The operands of an item -- rows b*L .. (+ntile*128), columns h*64 .. (+64) -- arrive as two groups of 128-row
   // boxes: the first rows of Q/K/V/dO are last read by the second-to-last pair, so the next item's first group is
@@ -173,10 +175,17 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     const int h = w % a.H, b = w / a.H;
     uint64_t* bar = buf ? bar_load1 : bar_load;
     mbar_expect_tx_e(bar, 4 * TILE * 128);
-    tma_load_2d_e(&tmQ, bar, smem + SM_Q + buf * 16384, h * HD, b * L + rg * TILE);
-    tma_load_2d_e(&tmK, bar, smem + SM_K + buf * 16384, h * HD, b * L + rg * TILE);
-    tma_load_2d_e(&tmV, bar, smem + SM_V + buf * 16384, h * HD, b * L + rg * TILE);
-    tma_load_2d_e(&tmdO, bar, smem + SM_DO + buf * 16384, h * HD, b * L + rg * TILE);
+    if (!pad) {
+      tma_load_2d_e(&tmQ, bar, smem + SM_Q + buf * 16384, h * HD, b * L + rg * TILE);
+      tma_load_2d_e(&tmK, bar, smem + SM_K + buf * 16384, h * HD, b * L + rg * TILE);
+      tma_load_2d_e(&tmV, bar, smem + SM_V + buf * 16384, h * HD, b * L + rg * TILE);
+      tma_load_2d_e(&tmdO, bar, smem + SM_DO + buf * 16384, h * HD, b * L + rg * TILE);
+    } else {          // head dim < 64: maps {hd, H, rows}, the 64-wide box is zero-filled past the head (full box bytes are counted)
+      tma_load_3d_e(&tmQ, bar, smem + SM_Q + buf * 16384, 0, h, b * L + rg * TILE);
+      tma_load_3d_e(&tmK, bar, smem + SM_K + buf * 16384, 0, h, b * L + rg * TILE);
+      tma_load_3d_e(&tmV, bar, smem + SM_V + buf * 16384, 0, h, b * L + rg * TILE);
+      tma_load_3d_e(&tmdO, bar, smem + SM_DO + buf * 16384, 0, h, b * L + rg * TILE);
+    }
   };
   // Single-tile items (L <= 128: text, MAE pass) use the two halves as a double buffer instead: item i lives in half
   // i & 1, so the next item's operands land while this one computes.
@@ -315,7 +324,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     int it = 0;
     for (int w = blockIdx.x; w + (int)gridDim.x < total; w += gridDim.x, ++it) {
       const int wn = w + gridDim.x;
-      if (!dbuf) {   // first touch of the next item goes to L2 now, a whole item ahead of the smem loads below
+      if (!dbuf && !pad) {   // first touch of the next item goes to L2 now, a whole item ahead of the smem loads below
         const int h = wn % a.H, b = wn / a.H;
         for (int g = 0; g < ntile; ++g) {
           tma_prefetch_2d_e(&tmQ, h * HD, b * L + g * TILE);
@@ -394,8 +403,9 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     };
     // bias gradient of the q / k / v projection = column sums of dQ / dK / dV over all rows: taken from the staged bf16 box
     // (rows past L hold exact zeros: their P / dS entries are masked), transposed read-back like the GEMM epilogue's
-    auto box_colsum = [&](float* out, bool live, int col0) {
+    auto box_colsum = [&](float* out, bool live, int colh, int h) {
       if (out == nullptr || !live) return;              // warp-uniform
+      const int col0 = h * a.hd + colh;
       __syncwarp();
       const int c4 = lane & 3;
       float cs[8];
@@ -419,21 +429,27 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         cs[k] += __shfl_xor_sync(0xffffffffu, cs[k], 8);
         cs[k] += __shfl_xor_sync(0xffffffffu, cs[k], 16);
       }
-      if (lane < 4) {
+      if (lane < 4 && colh + c4 * 8 < a.hd) {             // (columns past a padded head hold zeros: skipped)
         float* o = out + col0 + c4 * 8;
         asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(o), "f"(cs[0]), "f"(cs[1]), "f"(cs[2]), "f"(cs[3]) : "memory");
         asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(o + 4), "f"(cs[4]), "f"(cs[5]), "f"(cs[6]), "f"(cs[7]) : "memory");
       }
     };
-    auto release_and_store = [&](const CUtensorMap* map, bool live, int col0, int row0, int b) {
+    auto release_and_store = [&](const CUtensorMap* map, bool live, int colh, int h, int row0, int b) {
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       __syncwarp();
-      if (live) {                                         // warp-uniform; rows past L inside the box are clipped by the map
+      if (live && !pad) {                                 // warp-uniform; rows past L inside the box are clipped by the map
         asm volatile(
             "{\n\t.reg .pred e;\n\t"
             "elect.sync _|e, 0xffffffff;\n\t"
             "@e cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];\n\t}"
-            ::"l"((uint64_t)map), "r"(estage), "r"(col0), "r"(row0), "r"(b) : "memory");
+            ::"l"((uint64_t)map), "r"(estage), "r"(h * HD + colh), "r"(row0), "r"(b) : "memory");
+      } else if (live) {                                  // padded head: map {hd, H, L, B}, columns past the head clipped too
+        asm volatile(
+            "{\n\t.reg .pred e;\n\t"
+            "elect.sync _|e, 0xffffffff;\n\t"
+            "@e cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];\n\t}"
+            ::"l"((uint64_t)map), "r"(estage), "r"(colh), "r"(h), "r"(row0), "r"(b) : "memory");
       }
       bulk_commit();
     };
@@ -448,8 +464,8 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       tcgen05_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_dkv_free);
-      release_and_store(map, row0 < L, h * HD + (cg & 1) * 32, row0, b);
-      box_colsum(cg < 2 ? gd.dv_colsum : gd.dk_colsum, row0 < L, h * HD + (cg & 1) * 32);
+      release_and_store(map, row0 < L, (cg & 1) * 32, h, row0, b);
+      box_colsum(cg < 2 ? gd.dv_colsum : gd.dk_colsum, row0 < L, (cg & 1) * 32, h);
     };
     auto dq_epilogue = [&](int h, int b) {
       // dQ (TMEM lanes = queries): bar_dkv of the item's last key tile was committed after every MMA of the item;
@@ -461,8 +477,8 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       tcgen05_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_dq_free);
-      release_and_store(&tmGQ, live, h * HD + (cg & 1) * 32, row0, b);
-      box_colsum(gd.dq_colsum, live, h * HD + (cg & 1) * 32);
+      release_and_store(&tmGQ, live, (cg & 1) * 32, h, row0, b);
+      box_colsum(gd.dq_colsum, live, (cg & 1) * 32, h);
     };
     // The read-out of an item's last dV / dK and of its dQ is deferred until this warp has delivered the first tile of
     // the NEXT item, so the MMA pipe never waits for the drain (the control warp holds the next item's accumulating
@@ -629,18 +645,25 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   const int ntile = (L + TILE - 1) / TILE;
   const int npad = (L + 15) & ~15;                 // MMA N of S, MMA K of P V
   const int total = ntile * a.H * a.B;
+  const bool pad = a.hd != HD;                     // head dim 32 / 48 in zero-padded 64-wide tiles
 
   // (called by the whole control warp: one elected lane issues)
   auto issue_qk = [&](int w) {
     const int qt = w % ntile, h = (w / ntile) % a.H, b = w / (ntile * a.H);
     mbar_expect_tx_e(bar_load, TILE * 128 + ntile * TILE * 128);
-    tma_load_2d_e(&tmQ, bar_load, smem + F_SM_Q, h * HD, b * L + qt * TILE);
-    tma_load_2d_e(&tmK, bar_load, smem + F_SM_K, h * HD, b * L);
+    if (!pad) {
+      tma_load_2d_e(&tmQ, bar_load, smem + F_SM_Q, h * HD, b * L + qt * TILE);
+      tma_load_2d_e(&tmK, bar_load, smem + F_SM_K, h * HD, b * L);
+    } else {
+      tma_load_3d_e(&tmQ, bar_load, smem + F_SM_Q, 0, h, b * L + qt * TILE);
+      tma_load_3d_e(&tmK, bar_load, smem + F_SM_K, 0, h, b * L);
+    }
   };
   auto issue_v = [&](int w) {
     const int h = (w / ntile) % a.H, b = w / (ntile * a.H);
     mbar_expect_tx_e(bar_v, ntile * TILE * 128);
-    tma_load_2d_e(&tmV, bar_v, smem + F_SM_V, h * HD, b * L);
+    if (!pad) tma_load_2d_e(&tmV, bar_v, smem + F_SM_V, h * HD, b * L);
+    else tma_load_3d_e(&tmV, bar_v, smem + F_SM_V, 0, h, b * L);
   };
 
   if (threadIdx.x == F_NSOFT * 32) {
@@ -994,11 +1017,19 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
                 pack_bf16(o[8 * j + 6] * inv, o[8 * j + 7] * inv));
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       __syncwarp();
-      asm volatile(
-          "{\n\t.reg .pred e;\n\t"
-          "elect.sync _|e, 0xffffffff;\n\t"
-          "@e cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];\n\t}"
-          ::"l"((uint64_t)&tmO), "r"(ostage), "r"(h * HD), "r"(qt * TILE + warp * 32), "r"(b) : "memory");
+      if (!pad) {
+        asm volatile(
+            "{\n\t.reg .pred e;\n\t"
+            "elect.sync _|e, 0xffffffff;\n\t"
+            "@e cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];\n\t}"
+            ::"l"((uint64_t)&tmO), "r"(ostage), "r"(h * HD), "r"(qt * TILE + warp * 32), "r"(b) : "memory");
+      } else {
+        asm volatile(
+            "{\n\t.reg .pred e;\n\t"
+            "elect.sync _|e, 0xffffffff;\n\t"
+            "@e cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];\n\t}"
+            ::"l"((uint64_t)&tmO), "r"(ostage), "r"(0), "r"(h), "r"(qt * TILE + warp * 32), "r"(b) : "memory");
+      }
       bulk_commit();
       if (qi < L) a.lse[((long)b * a.H + h) * L + qi] = m * a.scale + logf(sum);
     }
@@ -1019,11 +1050,26 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
 
 extern void sc_count_kernel(int kind, int n);
 
+// Tensor maps of a head-padded operand (head dim 32 / 48): loads {hd, H, rows} with a 64 x 1 x box_rows box (zero fill past the
+// head), stores {hd, H, L, B} with a box_cols x 1 x 32 x 1 box (columns past the head and rows past the sample clipped).
+static int pad_load_map(const void* p, int hd, int H, long rows, long rs, uint32_t box_rows, CUtensorMap* out) {
+  const uint64_t dims[3] = {(uint64_t)hd, (uint64_t)H, (uint64_t)rows}, str[2] = {(uint64_t)hd, (uint64_t)rs};
+  const uint32_t box[3] = {64, 1, box_rows};
+  return sc_get_tensor_map_nd(p, 3, dims, str, box, 128, out);
+}
+static int pad_store_map(const void* p, int hd, int H, int L, int B, long rs, long bs, uint32_t box_cols, int swizzle, CUtensorMap* out) {
+  const uint64_t dims[4] = {(uint64_t)hd, (uint64_t)H, (uint64_t)L, (uint64_t)B}, str[3] = {(uint64_t)hd, (uint64_t)rs, (uint64_t)bs};
+  const uint32_t box[4] = {box_cols, 1, 32, 1};
+  return sc_get_tensor_map_nd(p, 4, dims, str, box, swizzle, out);
+}
+
 bool sc_attn_tc_supported(const sc_attn_desc* a) {
   auto packed = [&](const void* p, long bs, long rs, int L) {
     return ((uintptr_t)p & 15) == 0 && rs % 8 == 0 && bs == (long)L * rs;
   };
-  return a->dtype == SC_BF16 && a->hd == 64 && a->Lq == a->Lk && a->Lq >= 16 && a->Lq <= 256 && a->B <= 65535 &&
+  static const bool pad_ok = getenv("SC_ATT_TC_PAD") ? atoi(getenv("SC_ATT_TC_PAD")) != 0 : true;   // A/B switch: head dims < 64 on tcgen05
+  const bool hd_ok = a->hd == 64 || (pad_ok && (a->hd == 48 || a->hd == 32) && a->q_rs == a->k_rs && a->q_rs == a->v_rs);
+  return a->dtype == SC_BF16 && hd_ok && a->Lq == a->Lk && a->Lq >= 16 && a->Lq <= 256 && a->B <= 65535 &&
          packed(a->q, a->q_bs, a->q_rs, a->Lq) && packed(a->k, a->k_bs, a->k_rs, a->Lk) &&
          packed(a->v, a->v_bs, a->v_rs, a->Lk) && packed(a->o, a->o_bs, a->o_rs, a->Lq);
 }
@@ -1043,21 +1089,31 @@ int sc_attention_bwd_tc(const sc_attn_bwd_desc* g, float* delta, cudaStream_t st
   const long rows = (long)a->B * L;
   CUtensorMap tq, tk, tv, tdo;
   int rc;
-  // 2-D maps over the [B*L, H*64] column slices; box = 64 columns x 128 rows, zero fill past the last row
-  if ((rc = sc_get_tensor_map(a->q, (uint64_t)a->H * HD, rows, a->q_rs, 64, TILE, &tq))) return rc;
-  if ((rc = sc_get_tensor_map(a->k, (uint64_t)a->H * HD, rows, a->k_rs, 64, TILE, &tk))) return rc;
-  if ((rc = sc_get_tensor_map(a->v, (uint64_t)a->H * HD, rows, a->v_rs, 64, TILE, &tv))) return rc;
-  if ((rc = sc_get_tensor_map(g->d_o, (uint64_t)a->H * HD, rows, a->o_rs, 64, TILE, &tdo))) return rc;
-  // gradient outputs: 3-D {H*64, L, B}, 32 x 32 boxes, rows past L clipped
   CUtensorMap gq, gk, gv;
-  if ((rc = sc_get_tensor_map_3d(g->d_q, (uint64_t)a->H * HD, L, a->B, a->q_rs, a->q_bs, 32, 32, 64, &gq))) return rc;
-  if ((rc = sc_get_tensor_map_3d(g->d_k, (uint64_t)a->H * HD, L, a->B, a->k_rs, a->k_bs, 32, 32, 64, &gk))) return rc;
-  if ((rc = sc_get_tensor_map_3d(g->d_v, (uint64_t)a->H * HD, L, a->B, a->v_rs, a->v_bs, 32, 32, 64, &gv))) return rc;
+  if (a->hd == HD) {
+    // 2-D maps over the [B*L, H*64] column slices; box = 64 columns x 128 rows, zero fill past the last row
+    if ((rc = sc_get_tensor_map(a->q, (uint64_t)a->H * HD, rows, a->q_rs, 64, TILE, &tq))) return rc;
+    if ((rc = sc_get_tensor_map(a->k, (uint64_t)a->H * HD, rows, a->k_rs, 64, TILE, &tk))) return rc;
+    if ((rc = sc_get_tensor_map(a->v, (uint64_t)a->H * HD, rows, a->v_rs, 64, TILE, &tv))) return rc;
+    if ((rc = sc_get_tensor_map(g->d_o, (uint64_t)a->H * HD, rows, a->o_rs, 64, TILE, &tdo))) return rc;
+    // gradient outputs: 3-D {H*64, L, B}, 32 x 32 boxes, rows past L clipped
+    if ((rc = sc_get_tensor_map_3d(g->d_q, (uint64_t)a->H * HD, L, a->B, a->q_rs, a->q_bs, 32, 32, 64, &gq))) return rc;
+    if ((rc = sc_get_tensor_map_3d(g->d_k, (uint64_t)a->H * HD, L, a->B, a->k_rs, a->k_bs, 32, 32, 64, &gk))) return rc;
+    if ((rc = sc_get_tensor_map_3d(g->d_v, (uint64_t)a->H * HD, L, a->B, a->v_rs, a->v_bs, 32, 32, 64, &gv))) return rc;
+  } else {
+    if ((rc = pad_load_map(a->q, a->hd, a->H, rows, a->q_rs, TILE, &tq))) return rc;
+    if ((rc = pad_load_map(a->k, a->hd, a->H, rows, a->k_rs, TILE, &tk))) return rc;
+    if ((rc = pad_load_map(a->v, a->hd, a->H, rows, a->v_rs, TILE, &tv))) return rc;
+    if ((rc = pad_load_map(g->d_o, a->hd, a->H, rows, a->o_rs, TILE, &tdo))) return rc;
+    if ((rc = pad_store_map(g->d_q, a->hd, a->H, L, a->B, a->q_rs, a->q_bs, 32, 64, &gq))) return rc;
+    if ((rc = pad_store_map(g->d_k, a->hd, a->H, L, a->B, a->k_rs, a->k_bs, 32, 64, &gk))) return rc;
+    if ((rc = pad_store_map(g->d_v, a->hd, a->H, L, a->B, a->v_rs, a->v_bs, 32, 64, &gv))) return rc;
+  }
   sc_count_kernel(SC_K_ATTN_BWD_TC, g->delta_ready ? 1 : 2);
   if (!g->delta_ready) {         // (otherwise the out_proj dgrad that produced dO has already written it: sc_gemm dot_out)
     const long n = rows * a->H;
     attn_delta_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>((const bf16*)a->o, (const bf16*)g->d_o, a->o_bs, a->o_rs, a->B,
-                                                                   a->H, L, delta);
+                                                                   a->H, L, delta, a->hd);
   }
   const long items = (long)a->H * a->B;
   dim3 grid((unsigned)(items < sc_num_sms() ? items : sc_num_sms()));       // persistent: one CTA per SM
@@ -1079,11 +1135,18 @@ int sc_attention_fwd_tc(const sc_attn_desc* a, cudaStream_t st) {
   const long rows = (long)a->B * L;
   CUtensorMap tq, tk, tv;
   int rc;
-  if ((rc = sc_get_tensor_map(a->q, (uint64_t)a->H * HD, rows, a->q_rs, 64, TILE, &tq))) return rc;
-  if ((rc = sc_get_tensor_map(a->k, (uint64_t)a->H * HD, rows, a->k_rs, 64, ntile * TILE, &tk))) return rc;
-  if ((rc = sc_get_tensor_map(a->v, (uint64_t)a->H * HD, rows, a->v_rs, 64, ntile * TILE, &tv))) return rc;
   CUtensorMap to;
-  if ((rc = sc_get_tensor_map_3d(a->o, (uint64_t)a->H * HD, L, a->B, a->o_rs, a->o_bs, 64, 32, 128, &to))) return rc;
+  if (a->hd == HD) {
+    if ((rc = sc_get_tensor_map(a->q, (uint64_t)a->H * HD, rows, a->q_rs, 64, TILE, &tq))) return rc;
+    if ((rc = sc_get_tensor_map(a->k, (uint64_t)a->H * HD, rows, a->k_rs, 64, ntile * TILE, &tk))) return rc;
+    if ((rc = sc_get_tensor_map(a->v, (uint64_t)a->H * HD, rows, a->v_rs, 64, ntile * TILE, &tv))) return rc;
+    if ((rc = sc_get_tensor_map_3d(a->o, (uint64_t)a->H * HD, L, a->B, a->o_rs, a->o_bs, 64, 32, 128, &to))) return rc;
+  } else {
+    if ((rc = pad_load_map(a->q, a->hd, a->H, rows, a->q_rs, TILE, &tq))) return rc;
+    if ((rc = pad_load_map(a->k, a->hd, a->H, rows, a->k_rs, ntile * TILE, &tk))) return rc;
+    if ((rc = pad_load_map(a->v, a->hd, a->H, rows, a->v_rs, ntile * TILE, &tv))) return rc;
+    if ((rc = pad_store_map(a->o, a->hd, a->H, L, a->B, a->o_rs, a->o_bs, 64, 128, &to))) return rc;
+  }
   sc_count_kernel(SC_K_ATTN_FWD_TC, 1);
   const long total = (long)ntile * a->H * a->B;
   static const int online = getenv("SC_ATT_FWD_TWO_PASS") ? 0 : 1; // A/B switch: exact row maximum first (reads S twice)

@@ -150,6 +150,50 @@ int sc_get_tensor_map_3d(const void* ptr, uint64_t dim0, uint64_t dim1, uint64_t
   return SC_OK;
 }
 
+// bf16 tensor map of rank 3 or 4 with explicit dims / element strides (of dims 1..) / box: head-padded attention tiles -- the
+// head dimension is its own (innermost) tensor dimension, so a 64-wide box over a 48-wide head is zero-filled on loads and
+// clipped on stores.  Not cached by pointer alone: the key folds every field.
+int sc_get_tensor_map_nd(const void* ptr, int rank, const uint64_t* dims, const uint64_t* strides_elems, const uint32_t* boxd,
+                         int swizzle_bytes, CUtensorMap* out) {
+  static std::mutex mu;
+  static std::unordered_map<MapKey, CUtensorMap, MapKeyHash> cache;
+  uint64_t hd = 1469598103934665603ull, hs = 1469598103934665603ull;
+  for (int i = 0; i < rank; ++i) hd = (hd ^ dims[i]) * 1099511628211ull;
+  for (int i = 0; i + 1 < rank; ++i) hs = (hs ^ strides_elems[i]) * 1099511628211ull;
+  uint32_t hb0 = 2166136261u, hb1 = (uint32_t)rank;
+  for (int i = 0; i < rank; ++i) hb0 = (hb0 ^ boxd[i]) * 16777619u;
+  MapKey key{ptr, hd, dims[0] | (dims[rank - 1] << 32), hs, hb0, hb1, swizzle_bytes | (5 << 24)};
+  {
+    std::lock_guard<std::mutex> g(mu);
+    auto it = cache.find(key);
+    if (it != cache.end()) {
+      *out = it->second;
+      return SC_OK;
+    }
+  }
+  EncodeTiledFn enc = get_encode_fn();
+  if (!enc || rank < 3 || rank > 4) {
+    sc_set_error("cuTensorMapEncodeTiled not available from the CUDA driver (or bad rank %d)", rank);
+    return SC_ERR_CUDA;
+  }
+  cuuint64_t gdim[4], gstride[3];
+  cuuint32_t box[4], estr[4] = {1, 1, 1, 1};
+  for (int i = 0; i < rank; ++i) { gdim[i] = dims[i]; box[i] = boxd[i]; }
+  for (int i = 0; i + 1 < rank; ++i) gstride[i] = strides_elems[i] * 2;
+  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(ptr), gdim, gstride, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : (swizzle_bytes == 32 ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_128B),
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    sc_set_error("cuTensorMapEncodeTiled(rank %d) failed (%d): ptr=%p dims=(%llu,%llu,%llu) box=(%u,%u,%u)", rank, (int)r, ptr,
+                 (unsigned long long)dims[0], (unsigned long long)dims[1], (unsigned long long)dims[2], boxd[0], boxd[1], boxd[2]);
+    return SC_ERR_CUDA;
+  }
+  std::lock_guard<std::mutex> g(mu);
+  if (cache.size() > 65536) cache.clear();
+  cache[key] = *out;
+  return SC_OK;
+}
 
 // Picks the compile-time specialised epilogue (tc::EF_*) for a descriptor, or EF_GENERIC.
 int sc_select_epilogue(const sc_gemm_desc* d, int splits) {

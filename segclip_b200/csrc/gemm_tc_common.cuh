@@ -113,6 +113,14 @@ SC_DEVINL void tma_load_2d_e(const CUtensorMap* map, uint64_t* bar, void* dst, i
       ::"r"(smem_u32(dst)), "l"((uint64_t)map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
       : "memory");
 }
+SC_DEVINL void tma_load_3d_e(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1, int c2) {
+  asm volatile(
+      "{\n\t.reg .pred e;\n\t"
+      "elect.sync _|e, 0xffffffff;\n\t"
+      "@e cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];\n\t}"
+      ::"r"(smem_u32(dst)), "l"((uint64_t)map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
 SC_DEVINL void tma_prefetch_2d_e(const CUtensorMap* map, int c0, int c1) {
   asm volatile(
       "{\n\t.reg .pred e;\n\t"
@@ -689,4 +697,6 @@ int sc_get_tensor_map_any(const void* ptr, uint64_t dim0, uint64_t dim1, uint64_
                           int swizzle_bytes, int elem_bytes, CUtensorMap* out);
 int sc_get_tensor_map_3d(const void* ptr, uint64_t dim0, uint64_t dim1, uint64_t dim2, uint64_t stride1_elems,
                          uint64_t stride2_elems, uint32_t box0, uint32_t box1, int swizzle_bytes, CUtensorMap* out);
+int sc_get_tensor_map_nd(const void* ptr, int rank, const uint64_t* dims, const uint64_t* strides_elems, const uint32_t* boxd,
+                         int swizzle_bytes, CUtensorMap* out);
 int sc_select_epilogue(const sc_gemm_desc* d, int splits);

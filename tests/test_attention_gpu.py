@@ -123,3 +123,18 @@ def test_cross_attention_flat_kv_layout(dtype, S):
     assert rel(o, ref.detach()) < tol
     assert rel(dq, qf.grad) < tol, rel(dq, qf.grad)
     assert rel(dkv, kvf.grad) < tol, rel(dkv, kvf.grad)
+
+
+def test_padded_head_dims_run_on_tcgen05():
+    """Head dims 48 (MAE decoder, module_mae.py:110-135) and 32 run on the tcgen05 kernels in zero-padded 64-wide tiles: the
+    head is its own tensor-map dimension, so the TMA zero-fills the box past the head on loads and clips it on stores
+    (outputs, gradients and the fused in_proj bias-gradient column sums are checked by _run)."""
+    from segclip_b200 import _lib
+    k0 = _lib.kernel_launches()
+    _run(3, 8, 197, 48, torch.bfloat16, False, seed=7)
+    _run(40, 8, 197, 48, torch.bfloat16, False, seed=8)           # more items than CTAs: persistent loops
+    _run(2, 4, 77, 32, torch.bfloat16, True, seed=9)
+    _run(5, 6, 128, 48, torch.bfloat16, True, seed=10)
+    k1 = _lib.kernel_launches()
+    assert k1["attn_fwd_tc"] - k0["attn_fwd_tc"] == 4 and k1["attn_bwd_tc"] - k0["attn_bwd_tc"] == 4, (k0, k1)
+    assert k1["attn_mma"] == k0["attn_mma"], (k0, k1)
