@@ -300,3 +300,59 @@ def test_inference_path_matches_oracle(precision):
     ref = scale * so.l2_normalize(otx) @ so.l2_normalize(ox).t()
     assert rel(t2v, ref) < (tol if precision == "fp32" else 0.1) and torch.equal(v2t, t2v.T)
     assert model(batch["input_ids"], None, None, batch["image"]) is None          # eval forward() returns None (modeling.py:254-256)
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_training_steps_follow_the_oracle(precision):
+    """The whole loop a user of the reference runs (main_task_align.py:300-347) for a few steps: forward, backward, fused
+    AdaptAdamW step with gradient clipping and the logit_scale clamp, zero_grad -- against the CPU oracle driven by the
+    optimizer oracle (pinned to the reference's own AdaptAdamW class).  Catches what single-step parity cannot: stale bf16
+    weight shadows, gradient buffers not re-zeroed, optimizer state drift."""
+    import math
+    from oracle import optimizer_oracle as oo
+    from oracle import segclip_oracle as so
+    from segclip_b200.engine import FROZEN_STEM
+    from segclip_b200.optim import FusedAdaptAdamW
+    from tools.e2e_report import build_model
+    cfg = so.toy_config(use_mae=True, use_kl=True)
+    B, steps, lr = 4, 4, 2e-3
+    params = so.init_params(cfg, seed=31)
+    batch, noise = so.make_batch(cfg, B, seed=32)
+    hp = dict(t_total=-1, warmup=-1, b1=0.9, b2=0.98, eps=1e-6, lr_start=0.0, lr_end=0.0)
+    # ---- oracle loop
+    op = {k: v.clone() for k, v in params.items()}
+    names = [k for k, v in op.items() if v.is_floating_point() and k not in FROZEN_STEM]
+    state = [dict(step=0, exp_avg=torch.zeros_like(op[n]), exp_avg_sq=torch.zeros_like(op[n])) for n in names]
+    ls = names.index("clip.logit_scale")
+    want, forced_seq = [], []
+    for _ in range(steps):
+        loss, grads, info = so.loss_and_grads(op, batch, noise, cfg, "torch18_flat", frozen=FROZEN_STEM)
+        want.append(float(loss))
+        forced_seq.append(info)
+        plist = [op[n] for n in names]
+        oo.step(plist, [grads.get(n) for n in names], state, [(list(range(len(names))), lr, 0.01)], clip_grad=1.0,
+                clamp_max={ls: math.log(100)}, **hp)
+    # ---- CUDA loop
+    model = build_model(cfg, params, precision, "torch18_flat")
+    model.inject_noise({k: v.cuda() for k, v in noise.items()})
+    named = dict(model.named_parameters())
+    opt = FusedAdaptAdamW([dict(params=[named[n] for n in names], lr=lr, weight_decay=0.01)], lr=lr, warmup=-1, t_total=-1,
+                          b1=0.9, b2=0.98, e=1e-6, weight_decay=0.01, clip_grad=1.0, clamp_max={named["clip.logit_scale"]: math.log(100)})
+    ids = batch["input_ids"]
+    got = []
+    for k in range(steps):
+        if precision == "bf16":       # discrete decisions teacher-forced to the oracle's of the same step (SURVEY F8)
+            f = {"main": forced_seq[k]["assign_main"].cuda(), "pool": forced_seq[k]["pool_arg"].cuda(), "mae": forced_seq[k]["assign_mae"].cuda()}
+            model.force_assignment(f)
+        loss = model(ids, torch.zeros_like(ids), batch["attention_mask"], batch["image"], image_seg=batch["image_seg"])
+        loss.backward()
+        got.append(float(loss.detach()))
+        opt.step()
+        opt.zero_grad()
+    tol = 2e-4 if precision == "fp32" else 1e-2
+    for a, b in zip(got, want):
+        assert abs(a - b) <= tol * abs(b), (got, want)
+    assert abs(want[-1] - want[0]) > 20 * tol * abs(want[0]) or precision == "bf16", "the loss must move for the comparison to mean anything: %s" % want
+    if precision == "fp32":           # parameters after the last step (Adam normalises the update: absolute bound, 15 % of one step)
+        worst = max((float((named[n].detach().cpu() - op[n]).abs().max()), n) for n in names)
+        assert worst[0] <= 3e-4, worst
