@@ -272,6 +272,12 @@ def main():
     launches = (_lib.launch_count() - l0) // args.steps
     step(pinned, True)
     ms_e2e = timed(pinned, True, args.steps)          # clocks are sampled over both timed regions
+    # the same end-to-end step fed raw uint8 pixels (the library's optional input boundary, SURVEY 8(f) rank 3: 1 byte per pixel
+    # over PCIe, CLIP mean / std normalisation on the GPU) -- informational, the headline `e2e` is the reference's fp32 contract
+    pinned_u8 = dict(pinned)
+    pinned_u8["image"] = (torch.rand(host["image"].shape) * 255).to(torch.uint8).pin_memory()
+    step(pinned_u8, True)
+    ms_e2e_u8 = timed(pinned_u8, True, args.steps)
     ms_fwd = timed(resident, False, args.steps, fwd_only)      # forward tape only (north_star: >= 70 % on the forward)
     if world > 1:
         lt = torch.tensor([loss0], device=dev)
@@ -304,6 +310,10 @@ def main():
                 "h2d_bytes_per_step": int(host["input_ids"].numel() * 8 + host["image"].numel() * 4 +
                                           (host["image_seg"].numel() * 8 if args.heads else 0)),
                 "d2h_bytes_per_step": 4},
+        "e2e_uint8_input": {"value": B * world / (ms_e2e_u8 / 1e3), "unit": "pairs/s",
+                            "h2d_bytes_per_step": int(host["input_ids"].numel() * 8 + host["image"].numel() +
+                                                      (host["image_seg"].numel() * 8 if args.heads else 0)),
+                            "note": "optional uint8 image boundary (normalised on the device); not the headline"},
         "gpu_launches": int(launches),
         "clocks": clocks,
         "loss_step0": losses, "loss_finite": all(x == x and abs(x) != float("inf") for x in losses),
