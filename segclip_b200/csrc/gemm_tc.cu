@@ -382,7 +382,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       tcgen05_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BN + half * (BN / 2);
       const int mrow0 = mt * BM + quarter * 32;
-      const int l7 = lane & 7, l3 = lane >> 3;
 #pragma unroll 1
       for (int c = 0; c < BN / 2 / 32; ++c) {
         float v[32];
