@@ -110,6 +110,16 @@ __global__ void cast_multi_kernel(const sc_cast_item* __restrict__ items, int n_
   const sc_cast_item it = items[lo];
   long i = ((blk - it.first_block) * blockDim.x + threadIdx.x) * 4;
   const float* s = (const float*)it.src;
+  if (dst_dtype == SC_BF16 && i + 3 < it.n && (((uintptr_t)s | (uintptr_t)it.dst) & 15) == 0) {
+    // one 16-byte load, one 8-byte store per thread (the weights of a step: 0.6 GB read, 0.3 GB written)
+    const float4 v = *(const float4*)(s + i);
+    __nv_bfloat162 lo2 = __floats2bfloat162_rn(v.x, v.y), hi2 = __floats2bfloat162_rn(v.z, v.w);
+    uint2 u;
+    u.x = *(uint32_t*)&lo2;
+    u.y = *(uint32_t*)&hi2;
+    *(uint2*)((bf16*)it.dst + i) = u;
+    return;
+  }
   for (int j = 0; j < 4 && i + j < it.n; ++j) st_any(it.dst, i + j, dst_dtype, s[i + j]);
 }
 
